@@ -1,0 +1,158 @@
+/* ttsb200 — C ABI of the B200-native text->mel->waveform inference path.
+ *
+ * The reference (nipponjo/tts-arabic-pytorch) has no FFI: its operator boundary for this path is
+ * three Python callables. Each entry point below replaces one of them and is what
+ * a Python/ctypes (or any other FFI) binding of the reference would call instead:
+ *
+ *   ttsb_hifigan_*      replaces vocoder.hifigan.models.Generator.forward      (vocoder/hifigan/models.py:111-127)
+ *                       and the loader vocoder.load_hifigan                     (vocoder/__init__.py:3-20)
+ *   ttsb_fastpitch_*    replaces models.fastpitch.fastpitch.model.FastPitch.infer (models/fastpitch/fastpitch/model.py:351-409)
+ *   ttsb_conv1d_*       op-level entry used by the parity tests: one nn.Conv1d / nn.Linear /
+ *                       nn.ConvTranspose1d site                                 (vocoder/hifigan/models.py:26-44,98-100)
+ *
+ * Conventions
+ *   - plain C types only; every pointer named d_* is a DEVICE pointer owned by the caller,
+ *     h_* is a HOST pointer. `stream` is a cudaStream_t passed as void*.
+ *   - the library never allocates on the hot path: callers pass a workspace sized by
+ *     *_workspace_bytes(); weights are copied/packed once at *_create().
+ *   - every function returns 0 on success; on failure a non-zero code, and ttsb_last_error()
+ *     returns a thread-local message. Nothing here falls back to the CPU: without a CUDA device
+ *     *_create() fails.
+ */
+#ifndef TTSB200_H
+#define TTSB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ttsb_hifigan ttsb_hifigan_t;
+typedef struct ttsb_fastpitch ttsb_fastpitch_t;
+typedef struct ttsb_conv1d ttsb_conv1d_t;
+
+/* A named host fp32 tensor in the reference's own state_dict layout (after weight-norm has been
+ * folded, i.e. what remove_weight_norm() leaves: vocoder/__init__.py:19). */
+typedef struct {
+    const char* name;
+    const float* h_data;
+    int ndim;
+    int64_t shape[4];
+} ttsb_tensor_t;
+
+const char* ttsb_last_error(void);
+int ttsb_version(void);
+
+/* Runtime switches (also readable from the environment at load: TTSB_CONV_IMPL=tc|simt,
+ * TTSB_DESC_MODE=0..3). impl 0 = tcgen05 kernel, 1 = SIMT check kernel. */
+int ttsb_set_conv_impl(int impl);
+int ttsb_set_desc_mode(int mode);
+int ttsb_get_conv_impl(void);
+int ttsb_get_desc_mode(void);
+/* Number of kernels launched by this library since load (all streams). */
+int64_t ttsb_launch_count(void);
+/* Device-side error flag raised by bounded mbarrier waits (0 = none). Synchronises the device. */
+int ttsb_device_error_flag(int* h_flag);
+
+/* ---------------------------------------------------------------------------------------------
+ * HiFi-GAN V1 generator (config.json: upsample_rates/kernel_sizes, resblock kernel sizes and
+ * dilations, upsample_initial_channel; resblock type "1" only).
+ * --------------------------------------------------------------------------------------------- */
+typedef struct {
+    int num_mels;                 /* 80 */
+    int upsample_initial_channel; /* 512 */
+    int num_upsamples;            /* 4 */
+    int upsample_rates[8];
+    int upsample_kernel_sizes[8];
+    int num_kernels;              /* 3 */
+    int resblock_kernel_sizes[8];
+    int resblock_dilations[8][3];
+} ttsb_hifigan_config_t;
+
+int ttsb_hifigan_create(const ttsb_hifigan_config_t* cfg, const ttsb_tensor_t* weights, int n_weights,
+                        int device, ttsb_hifigan_t** out);
+void ttsb_hifigan_destroy(ttsb_hifigan_t* h);
+int ttsb_hifigan_hop(const ttsb_hifigan_t* h); /* samples per mel frame (256) */
+size_t ttsb_hifigan_workspace_bytes(const ttsb_hifigan_t* h, int B, int T);
+/* mel -> waveform for a padded batch. Exactly one of d_mel_f32 ([B,num_mels,T] fp32, the
+ * reference layout) or d_mel_cl ([B,T,128] fp16 channel-last, rows >= len zero) is non-NULL.
+ * d_lens [B] int32 frames per utterance (NULL = all T): every layer treats frames beyond an
+ * utterance's length as the zero padding the reference's per-utterance call would see
+ * (models/fastpitch/networks.py:340-345). d_wav: [B, T*hop] fp32, zero beyond len*hop. */
+int ttsb_hifigan_forward(ttsb_hifigan_t* h, const float* d_mel_f32, const void* d_mel_cl,
+                         const int32_t* d_lens, int B, int T, float* d_wav, void* d_workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * FastPitch (net_config of models/fastpitch/__init__.py:3-41; 1 attention head of 64).
+ * The call is split where the reference has data-dependent host decisions:
+ *   encode     ids -> encoder -> duration & pitch predictors        (model.py:364-371)
+ *   condition  (transformed) pitch -> pitch/energy embedding -> durations -> frame counts
+ *                                                                    (model.py:382-403, 68-79)
+ *   decode     length regulation -> decoder -> mel projection        (model.py:81-86, 405-409)
+ * Between condition and decode the caller reads max(dec_lens) — the same host sync the reference
+ * has at model.py:76.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct {
+    int n_mel_channels;  /* 80 */
+    int n_symbols;
+    int d_model;         /* 384 */
+    int n_layers_enc, n_layers_dec;
+    int d_head;          /* 64, one head */
+    int d_inner;         /* 1536 */
+    int conv_kernel;     /* 3 */
+    int pred_filter;     /* 256 */
+    int pred_kernel;     /* 3 */
+    int energy_conditioning;
+    int n_speakers;
+    float speaker_emb_weight;
+} ttsb_fastpitch_config_t;
+
+int ttsb_fastpitch_create(const ttsb_fastpitch_config_t* cfg, const ttsb_tensor_t* weights, int n_weights,
+                          int device, ttsb_fastpitch_t** out);
+void ttsb_fastpitch_destroy(ttsb_fastpitch_t* h);
+/* d_state: persistent between encode -> condition -> decode of one batch (token lengths,
+ * conditioned encoder output, cumulative durations). d_workspace: scratch, sized for
+ * max(L, T) rows; encode/condition need T = 0, decode needs the real T. */
+size_t ttsb_fastpitch_state_bytes(const ttsb_fastpitch_t* h, int B, int L);
+size_t ttsb_fastpitch_workspace_bytes(const ttsb_fastpitch_t* h, int B, int L, int T);
+
+/* d_ids [B,L] int64 (0 = padding, trailing only). Outputs: d_log_dur [B,L] fp32 (masked head
+ * output, before exp), d_pitch [B,L] fp32. speaker < 0 = no speaker embedding. */
+int ttsb_fastpitch_encode(ttsb_fastpitch_t* h, const int64_t* d_ids, int B, int L, int speaker,
+                          float* d_log_dur, float* d_pitch, void* d_state, void* d_workspace,
+                          size_t workspace_bytes, void* stream);
+/* d_pitch_in [B,L]: pitch track to embed (predicted, transformed or target). d_energy_tgt [B,L] or
+ * NULL (predict). d_dur_tgt [B,L] or NULL (use exp(log_dur)-1). Outputs: d_dur_pred [B,L],
+ * d_energy_pred [B,L] (untouched if no energy conditioning), d_dec_lens [B] int64. */
+int ttsb_fastpitch_condition(ttsb_fastpitch_t* h, int B, int L, const float* d_log_dur,
+                             const float* d_pitch_in, const float* d_energy_tgt, const float* d_dur_tgt,
+                             float pace, float max_duration, float* d_dur_pred, float* d_energy_pred,
+                             int64_t* d_dec_lens, void* d_state, void* d_workspace, size_t workspace_bytes,
+                             void* stream);
+/* T = max(dec_lens) read by the caller. d_mel [B,n_mel,T] fp32 (reference layout; frames beyond
+ * an utterance hold proj.bias exactly like the reference). d_mel_cl optional [B,T,128] fp16
+ * channel-last copy for ttsb_hifigan_forward (zero beyond each utterance), may be NULL. */
+int ttsb_fastpitch_decode(ttsb_fastpitch_t* h, int B, int L, int T, float* d_mel, void* d_mel_cl,
+                          void* d_state, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Single conv site, for parity tests of the dense-contraction kernel in isolation.
+ *   kind 0: nn.Conv1d     weight [Cout,Cin,K], stride 1, padding = dilation*(K-1)/2
+ *   kind 1: nn.ConvTranspose1d weight [Cin,Cout,K=2*stride], padding = stride/2
+ * --------------------------------------------------------------------------------------------- */
+int ttsb_conv1d_create(int kind, int cin, int cout, int ksize, int dilation, int stride,
+                       const float* h_weight, const float* h_bias, int device, ttsb_conv1d_t** out);
+void ttsb_conv1d_destroy(ttsb_conv1d_t* h);
+/* d_in: [B,T,cin_pad] fp16 channel-last (cin_pad = cin rounded up to 32/64 as reported by
+ * ttsb_conv1d_cin_pad). d_out: [B,T*stride,cout] fp16. Optional fused terms: d_residual (same shape
+ * as d_out), act_slope (<0: none; else leaky-relu slope applied to the output), d_lens. */
+int ttsb_conv1d_cin_pad(const ttsb_conv1d_t* h);
+int ttsb_conv1d_forward(ttsb_conv1d_t* h, const void* d_in, int B, int T, const void* d_residual,
+                        float act_slope, const int32_t* d_lens, void* d_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TTSB200_H */

@@ -1,0 +1,65 @@
+// Host-side description of one "row GEMM with taps": the single compute primitive behind every
+// dense contraction on the hot path.
+//
+//   out[b, t, n] = sum_{tap} sum_{ci} in[b, t + off(tap), ci] * W[n, tap, ci]      (+ fused epilogue)
+//
+// with channel-last fp16 activations in[B, T, ld] (rows outside [0, T) read as zero, i.e. the
+// zero padding of nn.Conv1d). Instances:
+//   nn.Conv1d (dilated)        hifigan/models.py:26-44,92,107  transformer.py:60-63  model.py:48-50
+//   nn.ConvTranspose1d         hifigan/models.py:98-100  -> two-tap polyphase form, N = stride*Cout
+//   nn.Linear                  transformer.py:105,108  model.py:127,231      -> one tap
+#pragma once
+#include <vector>
+#include "common.cuh"
+#include "epilogue.cuh"
+
+namespace ttsb {
+
+constexpr int kMaxTaps = 16;
+constexpr int kTileM = 128;  // output rows (time positions) per CTA
+
+struct ConvLayer {
+    // logical shape
+    int cin = 0;        // input channels as stored (multiple of chunk_k)
+    int n_total = 0;    // output columns (Cout, or stride*Cout for transposed conv)
+    int n_taps = 1;
+    int tap_off[2][kMaxTaps] = {};  // row offsets; class 1 used by N tiles >= class_split
+    int class_split = 1 << 30;
+    // tiling
+    int chunk_k = 64;   // K elements per smem row (64 -> 128B swizzle, 32 -> 64B swizzle)
+    int n_chunks = 0;
+    int n_tile = 0;     // columns per CTA
+    int n_sub = 1;      // MMA N splits inside a CTA (n_tile / n_sub <= 256)
+    int halo_lo = 0, halo_hi = 0;
+    int rows_panel = 0;
+    int a_slots = 0, b_stages = 0;
+    int tmem_cols = 0;
+    size_t smem_bytes = 0;
+    // device data
+    __half* w_packed = nullptr;  // [n_tiles][chunk][tap] tiles of n_tile x chunk_k, pre-swizzled
+    float* bias = nullptr;       // [n_total] or null
+    int n_tiles() const { return n_total / n_tile; }
+};
+
+// `w_logical` is a dense host array [n_total][n_taps][cin_logical] (fp32); channels
+// [cin_logical, cin) are zero padding. `bias` may be null.
+int conv_layer_create(ConvLayer& L, int cin_logical, int cin_stored, int n_total, int n_taps,
+                      const int* tap_off0, const int* tap_off1, int class_split,
+                      const float* w_logical, const float* bias, int n_tile_hint);
+void conv_layer_destroy(ConvLayer& L);
+
+enum ConvImpl : int { IMPL_TC = 0, IMPL_SIMT = 1 };
+
+struct ConvRuntime {
+    int impl = IMPL_TC;
+    int desc_mode = 1;          // A-descriptor base_offset rule for row-shifted tap views (see conv_tc.cu)
+    int* err_flag = nullptr;    // device int, set by kernels on protocol timeouts
+    float* simt_scratch = nullptr;
+    size_t simt_scratch_elems = 0;
+};
+
+// in: [B, T, ld_in] fp16 channel-last. epi.T / epi.n_total / epi.bias are filled from the layer.
+int conv_forward(const ConvLayer& L, const ConvRuntime& rt, const __half* in, int ld_in, int B,
+                 int T, EpiParams epi, cudaStream_t stream);
+
+}  // namespace ttsb

@@ -1,0 +1,187 @@
+// Row-wise fused epilogue shared by the tcgen05 conv kernel (accumulators in TMEM) and the SIMT
+// check kernel (accumulators in a global fp32 scratch). One thread owns one output row
+// (one time position of one utterance) and walks its N columns in groups of 32.
+//
+// What it fuses, per reference op site:
+//   bias                       nn.Conv1d / nn.Linear bias
+//   residual + LayerNorm       transformer.py:88,156 (post-LN), eps 1e-5
+//   relu -> LayerNorm          model.py:54-57 (ConvReLUNorm)
+//   head dot                   model.py:132 (TemporalPredictor.fc, 256 -> 1)
+//   row mask                   transformer.py:174,176 (`output *= mask`), model.py:132
+//   leaky-relu copy            hifigan/models.py:48,50,114 (activation of the *next* conv's input)
+//   MRF mean                   hifigan/models.py:116-122 (xs / num_kernels)
+//   transposed fp32 store      model.py:406-408 (proj + permute -> [B,80,T])
+#pragma once
+#include "common.cuh"
+
+namespace ttsb {
+
+enum MrfMode : int { MRF_NONE = 0, MRF_FIRST = 1, MRF_ADD = 2, MRF_LAST = 3 };
+
+struct EpiParams {
+    int T = 0;                      // rows per utterance in every row-indexed buffer below
+    int n_total = 0;                // logical GEMM width (all N tiles)
+    const int* lens = nullptr;      // [B] valid units per utterance, or null = no masking
+    int len_mul = 1;                // valid rows = lens[b] * len_mul
+    const float* bias = nullptr;    // [n_total]
+    const __half* residual = nullptr;
+    int ld_res = 0;
+    int pre_ln_relu = 0;
+    const float* ln_g = nullptr;    // LayerNorm over n_total columns (needs a single N tile)
+    const float* ln_b = nullptr;
+    float ln_eps = 1e-5f;
+    const float* head_w = nullptr;  // [n_total]; scalar head on the normalised row
+    float head_b = 0.f;
+    float* head_out = nullptr;      // [B*T]
+    int mrf_mode = MRF_NONE;
+    __half* mrf_buf = nullptr;      // [B*T, n_total]
+    float mrf_scale = 1.f;
+    __half* out_raw = nullptr;      // v
+    int ld_raw = 0;
+    __half* out_act = nullptr;      // lrelu(v, act_slope); slope 0 == relu
+    int ld_act = 0;
+    float act_slope = 0.f;
+    float* out_f32_t = nullptr;     // [B, n_store, T] fp32, transposed store
+    int n_store = 0;
+    int f32_unmasked = 0;           // out_f32_t receives the value before row masking
+};
+
+#ifdef __CUDACC__
+struct TmemAcc {
+    uint32_t taddr;  // lane base already folded in
+    __device__ __forceinline__ void load(int c0, float (&v)[32]) const { tmem_ld32(taddr + c0, v); }
+    __device__ __forceinline__ void store(int c0, const float (&v)[32]) const { tmem_st32(taddr + c0, v); }
+};
+struct GmemAcc {
+    float* row;  // this thread's row of the fp32 scratch, or null when the row is out of range
+    __device__ __forceinline__ void load(int c0, float (&v)[32]) const {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = row ? row[c0 + j] : 0.f;
+    }
+    __device__ __forceinline__ void store(int c0, const float (&v)[32]) const {
+        if (!row) return;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) row[c0 + j] = v[j];
+    }
+};
+
+__device__ __forceinline__ void load8h(const __half* p, float (&f)[8]) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    float2 a = unpack_half2(u.x), b = unpack_half2(u.y), c = unpack_half2(u.z), d = unpack_half2(u.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ void store8h(__half* p, const float* f) {
+    uint4 u;
+    u.x = pack_half2(f[0], f[1]); u.y = pack_half2(f[2], f[3]);
+    u.z = pack_half2(f[4], f[5]); u.w = pack_half2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+
+// b: utterance, t: row inside the utterance, row_ok: t < T (loads from the accumulator are
+// warp-collective, so out-of-range threads still walk the loop but never touch memory).
+// n_base: first logical column of this N tile; n_tile: its width (multiple of 32, or 16).
+template <class Acc>
+__device__ __forceinline__ void run_epilogue(const EpiParams& e, const Acc& acc, int b, int t,
+                                             bool row_ok, int n_base, int n_tile) {
+    const long row = static_cast<long>(b) * e.T + t;
+    bool in_len = true;
+    if (e.lens != nullptr && row_ok) in_len = t < e.lens[b] * e.len_mul;
+    const bool do_ln = e.ln_g != nullptr;
+
+    float mean = 0.f, rstd = 1.f;
+    if (do_ln) {
+        // pass 1: materialise z = acc + bias + residual (+relu), keep it in the accumulator store
+        float s1 = 0.f, s2 = 0.f;
+        for (int c0 = 0; c0 < n_tile; c0 += 32) {
+            float v[32];
+            __syncwarp();
+            acc.load(c0, v);
+            if (row_ok) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int n = n_base + c0 + g * 8;
+                    float r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                    if (e.residual) load8h(e.residual + row * e.ld_res + n, r);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float x = v[g * 8 + j] + (e.bias ? __ldg(e.bias + n + j) : 0.f) + r[j];
+                        if (e.pre_ln_relu) x = fmaxf(x, 0.f);
+                        v[g * 8 + j] = x;
+                        s1 += x;
+                        s2 += x * x;
+                    }
+                }
+            }
+            __syncwarp();
+            acc.store(c0, v);
+        }
+        mean = s1 / static_cast<float>(n_tile);
+        float var = s2 / static_cast<float>(n_tile) - mean * mean;
+        rstd = rsqrtf(fmaxf(var, 0.f) + e.ln_eps);
+    }
+
+    float head = 0.f;
+    for (int c0 = 0; c0 < n_tile; c0 += 32) {
+        float v[32];
+        __syncwarp();
+        acc.load(c0, v);
+        if (!row_ok) continue;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            if (c0 + g * 8 >= n_tile) break;  // n_tile == 16 case
+            const int n = n_base + c0 + g * 8;
+            float x[8];
+            if (do_ln) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    x[j] = (v[g * 8 + j] - mean) * rstd * __ldg(e.ln_g + n + j) + __ldg(e.ln_b + n + j);
+                    if (e.head_w) head += x[j] * __ldg(e.head_w + n + j);
+                }
+            } else {
+                float r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                if (e.residual) load8h(e.residual + row * e.ld_res + n, r);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    x[j] = v[g * 8 + j] + (e.bias ? __ldg(e.bias + n + j) : 0.f) + r[j];
+            }
+            if (e.out_f32_t && e.f32_unmasked) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (n + j < e.n_store)
+                        e.out_f32_t[(static_cast<long>(b) * e.n_store + n + j) * e.T + t] = x[j];
+            }
+            if (!in_len) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = 0.f;
+            }
+            if (e.mrf_mode != MRF_NONE) {
+                __half* mb = e.mrf_buf + row * e.n_total + n;
+                float m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                if (e.mrf_mode != MRF_FIRST) load8h(mb, m);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = m[j] + x[j] * e.mrf_scale;
+                if (e.mrf_mode != MRF_LAST) {
+                    store8h(mb, x);
+                    continue;
+                }
+            }
+            if (e.out_raw) store8h(e.out_raw + row * e.ld_raw + n, x);
+            if (e.out_f32_t && !e.f32_unmasked) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (n + j < e.n_store)
+                        e.out_f32_t[(static_cast<long>(b) * e.n_store + n + j) * e.T + t] = x[j];
+            }
+            if (e.out_act) {
+                float a[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[j] = lrelu(x[j], e.act_slope);
+                store8h(e.out_act + row * e.ld_act + n, a);
+            }
+        }
+    }
+    if (e.head_out && row_ok) e.head_out[row] = in_len ? head + e.head_b : 0.f;
+}
+#endif  // __CUDACC__
+
+}  // namespace ttsb

@@ -1,0 +1,374 @@
+// HBM-bound and small kernels: layout packing, embedding, attention, length regulation,
+// conv_post+tanh. See kernels.cuh for the reference op site each one replaces.
+#include "kernels.cuh"
+#include "epilogue.cuh"
+
+namespace ttsb {
+
+// ------------------------------------------------------------------------------------------------
+// pack_mel: [B,C,T] fp32 -> [B,T,ld] fp16 (transpose through smem, 32x32 tiles)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_mel_kernel(const float* __restrict__ mel,
+                                                       const int* __restrict__ lens, int C, int T,
+                                                       __half* __restrict__ out, int ld) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int len = lens ? lens[b] : T;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 rows per pass
+    for (int r = ty; r < 32; r += 8) {
+        const int c = c0 + r, t = t0 + tx;
+        tile[r][tx] = (c < C && t < T && t < len) ? mel[(static_cast<size_t>(b) * C + c) * T + t] : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int t = t0 + r, c = c0 + tx;
+        if (t < T && c < ld) out[(static_cast<size_t>(b) * T + t) * ld + c] = __float2half(tile[tx][r]);
+    }
+}
+
+int launch_pack_mel(const float* mel, const int* lens, int B, int C, int T, __half* out, int ld,
+                    cudaStream_t s) {
+    dim3 grid(ceil_div(T, 32), ceil_div(ld, 32), B);
+    pack_mel_kernel<<<grid, 256, 0, s>>>(mel, lens, C, T, out, ld);
+    count_launch();
+    TTSB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv_post + tanh: 256 samples per block, (256+6) x 32 activations staged in smem (pitch 33)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv_post_tanh_kernel(const __half* __restrict__ x,
+                                                             const float* __restrict__ w, float bias,
+                                                             const int* __restrict__ lens, int len_mul,
+                                                             int N, float* __restrict__ wav) {
+    __shared__ float sx[262 * 33];
+    __shared__ float sw[7 * 32];
+    const int b = blockIdx.y;
+    const int n0 = blockIdx.x * 256;
+    if (threadIdx.x < 224) sw[threadIdx.x] = w[threadIdx.x];
+    // 262 rows x 32 ch = 262 x 4 uint4
+    for (int i = threadIdx.x; i < 262 * 4; i += 256) {
+        const int r = i >> 2, q = i & 3;
+        const int n = n0 + r - 3;
+        float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (n >= 0 && n < N) load8h(x + (static_cast<size_t>(b) * N + n) * 32 + q * 8, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sx[r * 33 + q * 8 + j] = f[j];
+    }
+    __syncthreads();
+    const int n = n0 + threadIdx.x;
+    if (n >= N) return;
+    float acc = bias;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        const float* row = sx + (threadIdx.x + k) * 33;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc += row[c] * sw[k * 32 + c];
+    }
+    const int len = lens ? lens[b] * len_mul : N;
+    wav[static_cast<size_t>(b) * N + n] = n < len ? tanhf(acc) : 0.f;
+}
+
+int launch_conv_post_tanh(const __half* x, const float* w, float bias, const int* lens, int len_mul,
+                          int B, int N, float* wav, cudaStream_t s) {
+    dim3 grid(ceil_div(N, 256), B);
+    conv_post_tanh_kernel<<<grid, 256, 0, s>>>(x, w, bias, lens, len_mul, N, wav);
+    count_launch();
+    TTSB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// embedding + positional embedding
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float posemb_val(int pos, int j, int D, const float* inv_freq) {
+    // pos_emb = cat[sin(pos*inv_freq), cos(pos*inv_freq)] (transformer.py:42-44)
+    const int half = D / 2;
+    const float a = static_cast<float>(pos) * inv_freq[j < half ? j : j - half];
+    return j < half ? sinf(a) : cosf(a);
+}
+
+__global__ void embed_kernel(const int64_t* __restrict__ ids, const float* __restrict__ emb,
+                             const float* __restrict__ cond, const float* __restrict__ inv_freq,
+                             int L, int D, __half* __restrict__ out) {
+    const int row = blockIdx.x;  // b*L + l
+    const int l = row % L;
+    const int64_t id = ids[row];
+    const bool valid = id != 0;
+    for (int j = threadIdx.x; j < D; j += blockDim.x) {
+        float v = emb[id * D + j];
+        if (valid) v += posemb_val(l, j, D, inv_freq);
+        if (cond) v += cond[j];
+        out[static_cast<size_t>(row) * D + j] = __float2half(v);
+    }
+}
+
+int launch_embed(const int64_t* ids, const float* emb, const float* cond, const float* inv_freq,
+                    int B, int L, int D, __half* out, cudaStream_t s) {
+    embed_kernel<<<B * L, 128, 0, s>>>(ids, emb, cond, inv_freq, L, D, out);
+    count_launch();
+    TTSB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+__global__ void ids_to_lens_kernel(const int64_t* __restrict__ ids, int L, int* __restrict__ lens) {
+    const int b = blockIdx.x;
+    int cnt = 0;
+    for (int l = threadIdx.x; l < L; l += 32) cnt += ids[static_cast<size_t>(b) * L + l] != 0 ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (threadIdx.x == 0) lens[b] = cnt;
+}
+int launch_ids_to_lens(const int64_t* ids, int B, int L, int* lens, cudaStream_t s) {
+    ids_to_lens_kernel<<<B, 32, 0, s>>>(ids, L, lens);
+    count_launch();
+    TTSB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// attention: one CTA = 64 queries of one utterance; keys/values streamed in tiles of 64 with an
+// online softmax (no [S,S] score tensor in HBM, unlike transformer.py:131-141).
+// 256 threads as 16x16: thread (ty,tx) owns score rows 4ty..4ty+3, cols 4tx..4tx+3 of the tile,
+// and output rows 4ty.., head dims 4tx.. .
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) attention_kernel(const __half* __restrict__ qkv,
+                                                        const int* __restrict__ lens, int S,
+                                                        float scale, __half* __restrict__ out) {
+    extern __shared__ float att_smem[];
+    float (*sq)[65] = reinterpret_cast<float (*)[65]>(att_smem);
+    float (*sk)[65] = sq + 64;
+    float (*sv)[65] = sk + 64;
+    float (*sp)[65] = sv + 64;
+    const int b = blockIdx.y;
+    const int q0 = blockIdx.x * 64;
+    const int len = lens ? min(lens[b], S) : S;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const __half* base = qkv + static_cast<size_t>(b) * S * 192;
+
+    for (int i = threadIdx.x; i < 64 * 8; i += 256) {
+        const int r = i >> 3, c8 = i & 7;
+        float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (q0 + r < S) load8h(base + static_cast<size_t>(q0 + r) * 192 + c8 * 8, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sq[r][c8 * 8 + j] = f[j] * scale;
+    }
+    float m[4], lsum[4], o[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        m[i] = -INFINITY;
+        lsum[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+    }
+    for (int k0 = 0; k0 < len; k0 += 64) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 64 * 8; i += 256) {
+            const int r = i >> 3, c8 = i & 7;
+            float fk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, fv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (k0 + r < len) {
+                load8h(base + static_cast<size_t>(k0 + r) * 192 + 64 + c8 * 8, fk);
+                load8h(base + static_cast<size_t>(k0 + r) * 192 + 128 + c8 * 8, fv);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { sk[r][c8 * 8 + j] = fk[j]; sv[r][c8 * 8 + j] = fv[j]; }
+        }
+        __syncthreads();
+        float sc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sc[i][j] = 0.f;
+        for (int d = 0; d < 64; ++d) {
+            float qv[4], kv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { qv[i] = sq[ty * 4 + i][d]; kv[i] = sk[tx * 4 + i][d]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sc[i][j] += qv[i] * kv[j];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (k0 + tx * 4 + j >= len) sc[i][j] = -INFINITY;
+                mx = fmaxf(mx, sc[i][j]);
+            }
+            for (int off = 8; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+            const float m_new = fmaxf(m[i], mx);  // finite: every tile has >= 1 valid key
+            const float corr = __expf(m[i] - m_new);
+            float ps = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float p = __expf(sc[i][j] - m_new);
+                sp[ty * 4 + i][tx * 4 + j] = p;
+                ps += p;
+            }
+            for (int off = 8; off > 0; off >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, off);
+            lsum[i] = lsum[i] * corr + ps;
+            m[i] = m_new;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[i][j] *= corr;
+        }
+        __syncthreads();
+        for (int k = 0; k < 64; ++k) {
+            float pv[4], vv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { pv[i] = sp[ty * 4 + i][k]; vv[i] = sv[k][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[i][j] += pv[i] * vv[j];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int q = q0 + ty * 4 + i;
+        if (q >= S) continue;
+        const float inv = lsum[i] > 0.f ? 1.f / lsum[i] : 0.f;
+        __half2 h01 = __floats2half2_rn(o[i][0] * inv, o[i][1] * inv);
+        __half2 h23 = __floats2half2_rn(o[i][2] * inv, o[i][3] * inv);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h01);
+        u.y = *reinterpret_cast<uint32_t*>(&h23);
+        *reinterpret_cast<uint2*>(out + (static_cast<size_t>(b) * S + q) * 64 + tx * 4) = u;
+    }
+}
+
+static const int kAttSmem = 4 * 64 * 65 * sizeof(float);
+int launch_attention(const __half* qkv, const int* lens, int B, int S, float scale, __half* out,
+                     cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        TTSB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kAttSmem));
+        configured = true;
+    }
+    dim3 grid(ceil_div(S, 64), B);
+    attention_kernel<<<grid, 256, kAttSmem, s>>>(qkv, lens, S, scale, out);
+    count_launch();
+    TTSB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pitch / energy embedding add
+// ------------------------------------------------------------------------------------------------
+__global__ void scalar_embed_add_kernel(__half* __restrict__ x, const float* __restrict__ p,
+                                        const float* __restrict__ w, const float* __restrict__ bias,
+                                        const int* __restrict__ lens, int L, int D, int apply_mask) {
+    const int row = blockIdx.x;
+    const int b = row / L, l = row % L;
+    const float pm = l > 0 ? p[row - 1] : 0.f;
+    const float p0 = p[row];
+    const float pp = l + 1 < L ? p[row + 1] : 0.f;
+    const bool keep = !apply_mask || !lens || l < lens[b];
+    for (int j = threadIdx.x; j < D; j += blockDim.x) {
+        const size_t idx = static_cast<size_t>(row) * D + j;
+        float v = __half2float(x[idx]) + bias[j] + w[j * 3 + 0] * pm + w[j * 3 + 1] * p0 + w[j * 3 + 2] * pp;
+        x[idx] = __float2half(keep ? v : 0.f);
+    }
+}
+int launch_scalar_embed_add(__half* x, const float* p, const float* w, const float* bias,
+                            const int* lens, int B, int L, int D, int apply_mask, cudaStream_t s) {
+    scalar_embed_add_kernel<<<B * L, 128, 0, s>>>(x, p, w, bias, lens, L, D, apply_mask);
+    count_launch();
+    TTSB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// durations -> repeats -> cumulative offsets (one warp per utterance; L is a few hundred)
+// ------------------------------------------------------------------------------------------------
+__global__ void durations_kernel(const float* __restrict__ log_dur, const float* __restrict__ dur_tgt,
+                                 float pace, float max_duration, int L, float* __restrict__ dur_pred,
+                                 int* __restrict__ cum, int* __restrict__ dec_lens,
+                                 int64_t* __restrict__ dec_lens64) {
+    const int b = blockIdx.x;
+    const int lane = threadIdx.x;
+    int running = 0;
+    if (lane == 0) cum[static_cast<size_t>(b) * (L + 1)] = 0;
+    for (int l0 = 0; l0 < L; l0 += 32) {
+        const int l = l0 + lane;
+        int rep = 0;
+        if (l < L) {
+            const size_t idx = static_cast<size_t>(b) * L + l;
+            float d = 0.f;
+            if (log_dur) {
+                // dur_pred = clamp(exp(log_dur) - 1, 0, max_duration)   (model.py:368)
+                d = fminf(fmaxf(expf(log_dur[idx]) - 1.f, 0.f), max_duration);
+                if (dur_pred) dur_pred[idx] = d;
+            }
+            if (dur_tgt) d = dur_tgt[idx];
+            // reps = (dur / pace + 0.5).long()   (model.py:72-73; .long() truncates toward zero)
+            rep = static_cast<int>(d / pace + 0.5f);
+        }
+        int incl = rep;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        if (l < L) cum[static_cast<size_t>(b) * (L + 1) + l + 1] = running + incl;
+        running += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) {
+        dec_lens[b] = running;
+        if (dec_lens64) dec_lens64[b] = running;
+    }
+}
+int launch_durations(const float* log_dur, const float* dur_tgt, float pace, float max_duration,
+                     int B, int L, float* dur_pred, int* cum, int* dec_lens, int64_t* dec_lens64,
+                     cudaStream_t s) {
+    durations_kernel<<<B, 32, 0, s>>>(log_dur, dur_tgt, pace, max_duration, L, dur_pred, cum, dec_lens,
+                                      dec_lens64);
+    count_launch();
+    TTSB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// regulate: frame -> token gather (+ decoder positional embedding). One warp per frame row.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) regulate_kernel(const __half* __restrict__ enc,
+                                                       const int* __restrict__ cum,
+                                                       const int* __restrict__ dec_lens,
+                                                       const float* __restrict__ inv_freq, int L, int T,
+                                                       int D, __half* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (t >= T) return;
+    __half* orow = out + (static_cast<size_t>(b) * T + t) * D;
+    if (t >= dec_lens[b]) {
+        for (int j = lane * 8; j < D; j += 256) *reinterpret_cast<uint4*>(orow + j) = make_uint4(0, 0, 0, 0);
+        return;
+    }
+    // token i with cum[i] <= t < cum[i+1]  (model.py:82-83)
+    const int* c = cum + static_cast<size_t>(b) * (L + 1);
+    int lo = 0, hi = L;  // invariant: c[lo] <= t < c[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (c[mid] <= t) lo = mid; else hi = mid;
+    }
+    const __half* erow = enc + (static_cast<size_t>(b) * L + lo) * D;
+    for (int j = lane * 8; j < D; j += 256) {
+        float f[8];
+        load8h(erow + j, f);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) f[q] += posemb_val(t, j + q, D, inv_freq);
+        store8h(orow + j, f);
+    }
+}
+int launch_regulate(const __half* enc, const int* cum, const int* dec_lens, const float* inv_freq,
+                       int B, int L, int T, int D, __half* out, cudaStream_t s) {
+    dim3 grid(ceil_div(T, 4), B);
+    regulate_kernel<<<grid, 128, 0, s>>>(enc, cum, dec_lens, inv_freq, L, T, D, out);
+    count_launch();
+    TTSB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace ttsb
