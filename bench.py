@@ -92,6 +92,18 @@ class ClockSampler:
                 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
+def usable_cores():
+    """Host threads this process may actually use: affinity mask, capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    try:
+        q, p = open('/sys/fs/cgroup/cpu.max').read().split()
+        if q != 'max':
+            n = max(1, min(n, int(float(q) / float(p) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_reference_step(fsd, gsd_folded, ids):
     """The reference's CPU path, restated: FastPitch.infer on the padded batch, then the generator once
     per utterance (models/fastpitch/networks.py:322-350). Returns number of audio samples."""
@@ -111,7 +123,7 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = min(usable_cores(), 32)
     torch.set_num_threads(cores)
     fsd = synth.fastpitch_state_dict(1234)
     gsd = synth.fold_weight_norm(synth.hifigan_state_dict(1235))
@@ -278,12 +290,14 @@ def run_ours(args):
                      'share_of_step': voc_total_ms / ms_dev if ms_dev > 0 else None},
     }
     if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+        cores = min(usable_cores(), 32)     # torch CPU convs at batch 1 stop scaling well before this
         torch.set_num_threads(cores)
         gsd_f = synth.fold_weight_norm(gsd)
-        bs = args.cpu_sample or 4
+        t0 = time.perf_counter()
+        cpu_reference_step(fsd, gsd_f, ids_host[:1].clone())
+        per_utt = time.perf_counter() - t0
+        bs = args.cpu_sample or max(1, min(4, int(6.0 / max(per_utt, 1e-3))))
         ids = ids_host[:bs].clone()
-        cpu_reference_step(fsd, gsd_f, ids[:1])
         t0 = time.perf_counter()
         n, reps = 0, 0
         while time.perf_counter() - t0 < 12.0 and reps < 16:

@@ -163,7 +163,7 @@ def test_tcgen05_and_simt_paths_agree(vocoder):
         b = vocoder(mel, lens=lens).cpu().numpy()
     finally:
         lib.ttsb_set_conv_impl(impl0)
-    assert _rel_rms(a, b) < 5e-4
+    assert _rel_rms(a, b) < tol.WAV_REL_RMS
 
 
 def test_full_size_round_trip_properties(fp_const4, vocoder):

@@ -52,7 +52,7 @@ enum ConvImpl : int { IMPL_TC = 0, IMPL_SIMT = 1 };
 
 struct ConvRuntime {
     int impl = IMPL_TC;
-    int desc_mode = 1;          // A-descriptor base_offset rule for row-shifted tap views (see conv_tc.cu)
+    int desc_mode = 0;          // A-descriptor base_offset rule for row-shifted tap views (see conv_tc.cu)
     int* err_flag = nullptr;    // device int, set by kernels on protocol timeouts
     float* simt_scratch = nullptr;
     size_t simt_scratch_elems = 0;

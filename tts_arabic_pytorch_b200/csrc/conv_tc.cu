@@ -148,9 +148,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         for (int k = 0; k < ksteps; ++k) {
                             const uint32_t aa = a_addr + k * 32;
                             const uint32_t bb = b_addr + s * nsub_cols * row_bytes + k * 32;
-                            // Row-shifted views start off the swizzle-atom boundary; desc_mode 1/2
-                            // pass the phase as the descriptor's base_offset ((addr>>7)&7, or &3
-                            // for 64B swizzle), desc_mode 0 leaves it 0 (absolute-address swizzle),
+                            // Row-shifted views start off the swizzle-atom boundary. Measured on
+                            // B200 (profiles/r01_s1_probe_conv.json): the UMMA unit applies the
+                            // swizzle XOR to ABSOLUTE shared-memory address bits, so the view is
+                            // correct with base_offset = 0 (desc_mode 0, the default) and WRONG
+                            // with base_offset = (addr>>7)&7 (desc_mode 1/2, kept as probes).
                             // desc_mode 3 never shifts (per-tap TMA tiles, shift == 0).
                             const uint32_t boff = args.desc_mode == 1 ? ((aa >> 7) & 7u)
                                                   : args.desc_mode == 2 ? ((aa >> 7) & (row_bytes == 128 ? 7u : 3u))
