@@ -2,6 +2,7 @@
 // implementation, and dispatch for the "row GEMM with taps" primitive (conv.cuh).
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 #include "conv.cuh"
 
 namespace ttsb {
@@ -68,11 +69,14 @@ int conv_layer_create(ConvLayer& L, int cin_logical, int cin_stored, int n_total
     const size_t row_bytes = L.chunk_k * 2;
     const size_t panel = L.rows_panel * row_bytes;
     const size_t btile = n_tile * row_bytes;
-    const size_t budget = kSmemMax - 2048;
+    size_t budget = kSmemMax - 2048;
+    int max_b = 6;
+    if (const char* e = getenv("TTSB_SMEM_BUDGET")) budget = std::min(budget, static_cast<size_t>(atol(e)));
+    if (const char* e = getenv("TTSB_MAX_B_STAGES")) max_b = std::max(1, atoi(e));
     int a_slots = L.n_chunks;
     if (a_slots * panel + 2 * btile > budget) a_slots = std::min(L.n_chunks, 2);
     int b_stages = static_cast<int>((budget - a_slots * panel) / btile);
-    b_stages = std::min(b_stages, std::min(6, L.n_chunks * n_taps));
+    b_stages = std::min(b_stages, std::min(max_b, L.n_chunks * n_taps));
     TTSB_REQUIRE(b_stages >= 1 && a_slots >= 1, "tile does not fit in shared memory");
     L.a_slots = a_slots;
     L.b_stages = b_stages;

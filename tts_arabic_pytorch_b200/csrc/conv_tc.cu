@@ -19,6 +19,7 @@
 // Replaces (reference): cuDNN conv / cuBLAS GEMM calls behind nn.Conv1d, nn.ConvTranspose1d and
 // nn.Linear on the hot path (vocoder/hifigan/models.py:46-53,111-127, transformer.py:83-88,
 // 122,148, model.py:54-57,406).
+#include <cstdlib>
 #include "conv.cuh"
 
 namespace ttsb {
@@ -33,6 +34,7 @@ struct ConvTcArgs {
     int a_slots, b_stages;
     int class_split;
     int desc_mode;
+    int debug_flags;   // timing decomposition only: 1 = skip epilogue memory traffic, 2 = shrink weight loads
     int tap_off[2][kMaxTaps];
     const __half* w;
     int* err_flag;
@@ -115,10 +117,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     }
                     const int sb = i % args.b_stages, ub = i / args.b_stages;
                     mbar_wait(&empty_b[sb], (ub & 1) ^ 1, args.err_flag, 102);
-                    mbar_expect_tx(&full_b[sb], btile_bytes);
+                    const int bbytes = ((args.debug_flags & 2) && i >= args.b_stages) ? 16 : btile_bytes;
+                    mbar_expect_tx(&full_b[sb], bbytes);
                     bulk_load_1d(smem_b + sb * btile_bytes,
                                  wbase + static_cast<size_t>(i) * args.n_tile * args.chunk_k,
-                                 btile_bytes, &full_b[sb]);
+                                 bbytes, &full_b[sb]);
                 }
             }
         }
@@ -175,7 +178,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         mbar_wait(tmem_full, 0, args.err_flag, 105);
         tc_fence_after();
         TmemAcc acc{tmem_base + (static_cast<uint32_t>(q * 32) << 16)};
-        run_epilogue(args.epi, acc, b, t, t < args.T, ntile * args.n_tile, args.n_tile);
+        if (args.debug_flags & 1) {
+            float v[32];
+            acc.load(0, v);
+            if (v[0] == 1234.5678f && args.epi.out_raw) args.epi.out_raw[0] = __float2half(v[1]);
+        } else {
+            run_epilogue(args.epi, acc, b, t, t < args.T, ntile * args.n_tile, args.n_tile);
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -255,6 +264,10 @@ int conv_forward_tc(const ConvLayer& L, const ConvRuntime& rt, const __half* in,
     a.n_tile = L.n_tile; a.n_sub = L.n_sub;
     a.a_slots = a_slots; a.b_stages = b_stages;
     a.class_split = L.class_split; a.desc_mode = rt.desc_mode;
+    {
+        static int dbg = getenv("TTSB_DEBUG_FLAGS") ? atoi(getenv("TTSB_DEBUG_FLAGS")) : 0;
+        a.debug_flags = dbg;
+    }
     for (int c = 0; c < 2; ++c)
         for (int i = 0; i < kMaxTaps; ++i) a.tap_off[c][i] = L.tap_off[c][i];
     a.w = L.w_packed; a.err_flag = rt.err_flag; a.epi = epi;
