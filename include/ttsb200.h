@@ -52,6 +52,9 @@ int ttsb_get_conv_impl(void);
 int ttsb_get_desc_mode(void);
 /* Number of kernels launched by this library since load (all streams). */
 int64_t ttsb_launch_count(void);
+/* Debug: device buffer of 256 x 64 int64 that conv_tc_kernel fills with clock64() stamps per CTA
+ * (NULL disables). Slot meaning in csrc/conv_tc.cu (tl_mark). Not for production use. */
+int ttsb_debug_set_timeline(void* d_buf);
 /* Device-side error flag raised by bounded mbarrier waits (0 = none). Synchronises the device. */
 int ttsb_device_error_flag(int* h_flag);
 

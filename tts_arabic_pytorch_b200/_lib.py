@@ -43,6 +43,7 @@ _SIGNATURES = {
     'ttsb_get_desc_mode': (c_int, []),
     'ttsb_launch_count': (c_int64, []),
     'ttsb_device_error_flag': (c_int, [ctypes.POINTER(c_int)]),
+    'ttsb_debug_set_timeline': (c_int, [c_void_p]),
     'ttsb_hifigan_create': (c_int, [ctypes.POINTER(HifiganConfig), ctypes.POINTER(TensorDesc), c_int, c_int,
                                     ctypes.POINTER(c_void_p)]),
     'ttsb_hifigan_destroy': (None, [c_void_p]),

@@ -37,6 +37,11 @@ int ttsb_device_error_flag(int* h_flag) {
     return 0;
 }
 
+int ttsb_debug_set_timeline(void* d_buf) {
+    global_runtime().timeline = static_cast<long long*>(d_buf);
+    return 0;
+}
+
 int ttsb_conv1d_create(int kind, int cin, int cout, int ksize, int dilation, int stride,
                        const float* h_weight, const float* h_bias, int device, ttsb_conv1d_t** out) {
     TTSB_REQUIRE(h_weight && out, "null argument");

@@ -56,6 +56,7 @@ struct ConvRuntime {
     int* err_flag = nullptr;    // device int, set by kernels on protocol timeouts
     float* simt_scratch = nullptr;
     size_t simt_scratch_elems = 0;
+    long long* timeline = nullptr;  // debug timeline buffer (256 CTAs x 64 slots) or null
 };
 
 // in: [B, T, ld_in] fp16 channel-last. epi.T / epi.n_total / epi.bias are filled from the layer.

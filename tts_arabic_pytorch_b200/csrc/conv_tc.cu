@@ -38,6 +38,7 @@ struct ConvTcArgs {
     int tap_off[2][kMaxTaps];
     const __half* w;
     int* err_flag;
+    long long* timeline;   // debug: 64 clock64() slots per CTA for the first 256 CTAs, or null
     EpiParams epi;
 };
 
@@ -51,6 +52,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t row_bytes
     d |= static_cast<uint64_t>(base_off & 7) << 49;
     d |= static_cast<uint64_t>(row_bytes == 128 ? 2 : 4) << 61;  // SWIZZLE_128B / SWIZZLE_64B
     return d;
+}
+
+__device__ __forceinline__ void tl_mark(const ConvTcArgs& a, int slot) {
+    if (a.timeline == nullptr) return;
+    const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    if (cta < 256 && slot < 64) a.timeline[cta * 64 + slot] = clock64();
 }
 
 template <int kTmemCols>
@@ -80,6 +87,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int b = blockIdx.z;
 
     if (warp == 0 && lane == 0) {
+        tl_mark(args, 0);
         tma_prefetch_desc(&tmap_a);
         for (int i = 0; i < args.a_slots; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
         for (int i = 0; i < args.b_stages; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
@@ -91,6 +99,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) tl_mark(args, 1);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -122,8 +131,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     bulk_load_1d(smem_b + sb * btile_bytes,
                                  wbase + static_cast<size_t>(i) * args.n_tile * args.chunk_k,
                                  bbytes, &full_b[sb]);
+                    if (i == 0) tl_mark(args, 2);
                 }
             }
+            tl_mark(args, 3);
         }
     } else if (warp == 1) {
         if (lane == 0) {
@@ -144,6 +155,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     const int sb = i % args.b_stages, ub = i / args.b_stages;
                     mbar_wait(&full_b[sb], ub & 1, args.err_flag, 104);
                     tc_fence_after();
+                    tl_mark(args, 8 + (i < 40 ? i : 40));
                     const int shift = per_tap ? 0 : args.halo_lo + args.tap_off[cls][tap];
                     const uint32_t a_addr = smem_u32(smem_a + sa * panel_bytes) + shift * row_bytes;
                     const uint32_t b_addr = smem_u32(smem_b + sb * btile_bytes);
@@ -170,6 +182,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 if (!per_tap) umma_commit(&empty_a[sa]);
             }
             umma_commit(tmem_full);
+            tl_mark(args, 4);
         }
     } else {
         // ---------------- epilogue: 4 warps x 32 lanes = 128 rows ----------------
@@ -177,6 +190,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int t = t0 + q * 32 + lane;
         mbar_wait(tmem_full, 0, args.err_flag, 105);
         tc_fence_after();
+        if (threadIdx.x == 64) tl_mark(args, 5);
         TmemAcc acc{tmem_base + (static_cast<uint32_t>(q * 32) << 16)};
         if (args.debug_flags & 1) {
             float v[32];
@@ -186,9 +200,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             run_epilogue(args.epi, acc, b, t, t < args.T, ntile * args.n_tile, args.n_tile);
         }
     }
+    if (threadIdx.x == 64) tl_mark(args, 6);
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc<kTmemCols>(tmem_base);
+    if (threadIdx.x == 64) tl_mark(args, 7);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -271,6 +287,7 @@ int conv_forward_tc(const ConvLayer& L, const ConvRuntime& rt, const __half* in,
     for (int c = 0; c < 2; ++c)
         for (int i = 0; i < kMaxTaps; ++i) a.tap_off[c][i] = L.tap_off[c][i];
     a.w = L.w_packed; a.err_flag = rt.err_flag; a.epi = epi;
+    a.timeline = rt.timeline;
 
     dim3 grid(ceil_div(T, kTileM), L.n_tiles(), B);
     switch (L.tmem_cols) {

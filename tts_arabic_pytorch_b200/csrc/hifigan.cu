@@ -64,6 +64,7 @@ int get_conv_runtime(size_t simt_elems, ConvRuntime& rt) {
     rt.err_flag = g.err_flag;
     rt.simt_scratch = g.simt_scratch;
     rt.simt_scratch_elems = g.simt_scratch_elems;
+    rt.timeline = g.timeline;
     return 0;
 }
 

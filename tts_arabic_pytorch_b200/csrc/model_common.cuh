@@ -16,6 +16,7 @@ struct GlobalRuntime {
     int* err_flag = nullptr;
     float* simt_scratch = nullptr;
     size_t simt_scratch_elems = 0;
+    long long* timeline = nullptr;
 };
 GlobalRuntime& global_runtime();
 // Returns a ConvRuntime view; for the SIMT path makes sure the fp32 scratch holds `elems` floats.
