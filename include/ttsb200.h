@@ -48,6 +48,8 @@ int ttsb_version(void);
  * TTSB_DESC_MODE=0..3). impl 0 = tcgen05 kernel, 1 = SIMT check kernel. */
 int ttsb_set_conv_impl(int impl);
 int ttsb_set_desc_mode(int mode);
+/* tcgen05 kernel generation: 2 = persistent conv_tc2 (default), 1 = one-tile-per-CTA conv_tc (cross-check). */
+int ttsb_set_tc_version(int v);
 int ttsb_get_conv_impl(void);
 int ttsb_get_desc_mode(void);
 /* Number of kernels launched by this library since load (all streams). */

@@ -13,8 +13,8 @@ def all_ok(v):
     return bool(c) and all(x.get('ok') for x in c.values()) and s[v].get('device_flag', 1) == 0
 
 
-for v in ['tc1', 'tc2', 'tc0', 'tc3']:
+for v in ['v2', 'v1']:
     if all_ok(v):
-        print('export TTSB_CONV_IMPL=tc TTSB_DESC_MODE=%s' % v[2:])
+        print('export TTSB_CONV_IMPL=tc TTSB_DESC_MODE=0 TTSB_TC_VERSION=%s' % v[1])
         sys.exit(0)
 print('export TTSB_CONV_IMPL=simt')

@@ -46,13 +46,17 @@ def child(variant):
     lib = _lib.load()
     if variant == 'simt':
         _lib.check(lib.ttsb_set_conv_impl(1))
+    elif variant in ('v1', 'v2'):
+        _lib.check(lib.ttsb_set_conv_impl(0))
+        _lib.check(lib.ttsb_set_desc_mode(0))
+        _lib.check(lib.ttsb_set_tc_version(int(variant[1])))
     else:
         _lib.check(lib.ttsb_set_conv_impl(0))
         _lib.check(lib.ttsb_set_desc_mode(int(variant[2:])))
     dev = torch.device('cuda:0')
     g = torch.Generator().manual_seed(0)
     results = {}
-    B, T = 2, 300
+    B, T = 3, 700      # several row tiles per utterance and a ragged tail; persistent CTAs wrap around
     for name, kind, cin, cout, k, dil, stride in CASES:
         wshape = (cout, cin, k) if kind == 0 else (cin, cout, k)
         w = (torch.randn(wshape, generator=g) / (cin * (k if kind == 0 else k / stride)) ** 0.5).half().float()
@@ -63,8 +67,9 @@ def child(variant):
         cpad = lib.ttsb_conv1d_cin_pad(h)
         x = torch.zeros(B, T, cpad, dtype=torch.float16)
         x[:, :, :cin] = torch.randn(B, T, cin, generator=g).half()
-        lens = torch.tensor([T, T - 37], dtype=torch.int32)
+        lens = torch.tensor([T, T - 37, 129], dtype=torch.int32)
         x[1, T - 37:] = 0
+        x[2, 129:] = 0
         n_out = cout * (stride if kind == 1 else 1)
         res = torch.randn(B, T, n_out, generator=g).half()
         xd, rd, ld = x.to(dev), res.to(dev), lens.to(dev)
@@ -114,7 +119,8 @@ def main():
     out_dir = os.path.join(REPO, 'gpurun_out')
     os.makedirs(out_dir, exist_ok=True)
     summary = {}
-    for variant in ['simt', 'tc1', 'tc2', 'tc0', 'tc3']:
+    variants = sys.argv[1:] if len(sys.argv) > 1 else ['simt', 'v2', 'v1']
+    for variant in variants:
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), '--child', variant], capture_output=True,
                                text=True, timeout=240)

@@ -39,6 +39,7 @@ _SIGNATURES = {
     'ttsb_version': (c_int, []),
     'ttsb_set_conv_impl': (c_int, [c_int]),
     'ttsb_set_desc_mode': (c_int, [c_int]),
+    'ttsb_set_tc_version': (c_int, [c_int]),
     'ttsb_get_conv_impl': (c_int, []),
     'ttsb_get_desc_mode': (c_int, []),
     'ttsb_launch_count': (c_int64, []),

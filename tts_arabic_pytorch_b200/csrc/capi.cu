@@ -24,6 +24,11 @@ int ttsb_set_desc_mode(int mode) {
     global_runtime().desc_mode = mode;
     return 0;
 }
+int ttsb_set_tc_version(int v) {
+    TTSB_REQUIRE(v == 1 || v == 2, "tc version must be 1 (one tile per CTA) or 2 (persistent)");
+    global_runtime().tc_version = v;
+    return 0;
+}
 int ttsb_get_conv_impl(void) { return global_runtime().impl; }
 int ttsb_get_desc_mode(void) { return global_runtime().desc_mode; }
 int64_t ttsb_launch_count(void) { return launch_count(); }

@@ -35,6 +35,9 @@ struct ConvLayer {
     int a_slots = 0, b_stages = 0;
     int tmem_cols = 0;
     size_t smem_bytes = 0;
+    // persistent kernel (conv_tc2) plan
+    int a_slots2 = 0, b_stages2 = 0, acc_bufs = 1, occ2 = 1, tmem_cols2 = 0;
+    size_t smem_bytes2 = 0;
     // device data
     __half* w_packed = nullptr;  // [n_tiles][chunk][tap] tiles of n_tile x chunk_k, pre-swizzled
     float* bias = nullptr;       // [n_total] or null
@@ -52,6 +55,7 @@ enum ConvImpl : int { IMPL_TC = 0, IMPL_SIMT = 1 };
 
 struct ConvRuntime {
     int impl = IMPL_TC;
+    int tc_version = 2;         // 2 = persistent conv_tc2 kernel, 1 = one-tile-per-CTA conv_tc kernel
     int desc_mode = 0;          // A-descriptor base_offset rule for row-shifted tap views (see conv_tc.cu)
     int* err_flag = nullptr;    // device int, set by kernels on protocol timeouts
     float* simt_scratch = nullptr;

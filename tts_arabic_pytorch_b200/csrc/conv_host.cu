@@ -17,6 +17,8 @@ long long launch_count() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED)
 
 int conv_forward_tc(const ConvLayer& L, const ConvRuntime& rt, const __half* in, int ld_in, int B,
                     int T, const EpiParams& epi, cudaStream_t stream);
+int conv_forward_tc2(const ConvLayer& L, const ConvRuntime& rt, const __half* in, int ld_in, int B,
+                     int T, const EpiParams& epi, cudaStream_t stream);
 
 // Byte offset of element (n, kk) inside one pre-swizzled n_tile x chunk_k weight tile.
 // Rows are chunk_k*2 bytes; 16-byte chunks are XOR-swizzled with the row phase exactly like the
@@ -81,6 +83,30 @@ int conv_layer_create(ConvLayer& L, int cin_logical, int cin_stored, int n_total
     L.a_slots = a_slots;
     L.b_stages = b_stages;
     L.smem_bytes = 1024 + a_slots * panel + b_stages * btile + (2 * a_slots + 2 * b_stages + 1) * 8 + 16;
+
+    // persistent-kernel plan: two CTAs per SM for light tiles (HBM-bound stages), one CTA with deep
+    // rings otherwise; accumulators double-buffered in TMEM when two tiles fit in 512 columns
+    {
+        L.acc_bufs = 2 * n_tile <= 512 ? 2 : 1;
+        L.tmem_cols2 = 32;
+        while (L.tmem_cols2 < L.acc_bufs * n_tile) L.tmem_cols2 *= 2;
+        const size_t full = kSmemMax - 2048;
+        const size_t half = 110 * 1024;
+        const int total_b = L.n_chunks * n_taps;
+        const bool light = L.n_chunks * panel + std::min(4, total_b) * btile <= half && L.tmem_cols2 <= 256;
+        L.occ2 = light ? 2 : 1;
+        if (const char* e = getenv("TTSB_OCC2")) L.occ2 = std::max(1, std::min(atoi(e), light ? 4 : 1));
+        const size_t bud = std::min(budget, L.occ2 >= 2 ? (kSmemMax / L.occ2 - 3072) : full);
+        int as2 = L.n_chunks;
+        if (as2 * panel + 2 * btile > bud) as2 = std::min(L.n_chunks, 2);
+        if (2 * L.n_chunks * panel + std::min(4, total_b) * btile <= bud) as2 = 2 * L.n_chunks;
+        int bs2 = static_cast<int>((bud - as2 * panel) / btile);
+        bs2 = std::min(bs2, std::min(std::max(max_b, 8), total_b));
+        TTSB_REQUIRE(bs2 >= 1 && as2 >= 1, "persistent tile does not fit in shared memory");
+        L.a_slots2 = as2;
+        L.b_stages2 = bs2;
+        L.smem_bytes2 = 1024 + as2 * panel + bs2 * btile + (2 * as2 + 2 * bs2 + 4) * 8 + 16;
+    }
 
     // pack weights: [n_tiles][chunk][tap] tiles, fp16, swizzled
     const size_t tile_elems = static_cast<size_t>(n_tile) * L.chunk_k;
@@ -187,7 +213,7 @@ __global__ void __launch_bounds__(128) conv_simt_epilogue_kernel(const EpiParams
     const int t = blockIdx.x * 128 + threadIdx.x;
     const bool ok = t < e.T;
     GmemAcc acc{ok ? scratch + (static_cast<size_t>(b) * e.T + t) * e.n_total + ntile * n_tile : nullptr};
-    run_epilogue(e, acc, b, t, ok, ntile * n_tile, n_tile);
+    run_epilogue(e, acc, b, t, ok, ntile * n_tile, n_tile, [] {});
 }
 
 static int conv_forward_simt(const ConvLayer& L, const ConvRuntime& rt, const __half* in, int ld_in,
@@ -220,6 +246,7 @@ int conv_forward(const ConvLayer& L, const ConvRuntime& rt, const __half* in, in
     if (!epi.bias) epi.bias = L.bias;
     if (epi.ln_g) TTSB_REQUIRE(L.n_tiles() == 1, "LayerNorm epilogue needs the whole row in one CTA");
     if (rt.impl == IMPL_SIMT) return conv_forward_simt(L, rt, in, ld_in, B, T, epi, stream);
+    if (rt.tc_version == 2) return conv_forward_tc2(L, rt, in, ld_in, B, T, epi, stream);
     return conv_forward_tc(L, rt, in, ld_in, B, T, epi, stream);
 }
 

@@ -188,16 +188,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // ---------------- epilogue: 4 warps x 32 lanes = 128 rows ----------------
         const int q = warp & 3;
         const int t = t0 + q * 32 + lane;
-        mbar_wait(tmem_full, 0, args.err_flag, 105);
-        tc_fence_after();
-        if (threadIdx.x == 64) tl_mark(args, 5);
         TmemAcc acc{tmem_base + (static_cast<uint32_t>(q * 32) << 16)};
+        auto wait_acc = [&] {
+            mbar_wait(tmem_full, 0, args.err_flag, 105);
+            tc_fence_after();
+            if (threadIdx.x == 64) tl_mark(args, 5);
+        };
         if (args.debug_flags & 1) {
+            wait_acc();
             float v[32];
             acc.load(0, v);
             if (v[0] == 1234.5678f && args.epi.out_raw) args.epi.out_raw[0] = __float2half(v[1]);
         } else {
-            run_epilogue(args.epi, acc, b, t, t < args.T, ntile * args.n_tile, args.n_tile);
+            run_epilogue(args.epi, acc, b, t, t < args.T, ntile * args.n_tile, args.n_tile, wait_acc);
         }
     }
     if (threadIdx.x == 64) tl_mark(args, 6);

@@ -1,0 +1,295 @@
+// conv_tc2: persistent, warp-specialised tcgen05 kernel for "row GEMM with taps" (conv.cuh).
+//
+// Same math, data layout and smem/TMEM operand scheme as conv_tc.cu (v1: one tile per CTA, kept as
+// a cross-check); what changes is the schedule, driven by the v1 in-kernel timeline
+// (profiles/r01_s3_timeline.txt): v1 spent ~860 cycles of scalar bookkeeping per (chunk, tap)
+// iteration in the single MMA-issuing thread, ~2500 cycles of per-CTA setup, and an epilogue that
+// serialised ~16 dependent global loads after the accumulator was ready.
+//
+//   * one persistent CTA per SM slot; a CTA owns ONE N tile and walks (utterance, row-tile) work
+//     items with stride = #CTAs of that N tile; barriers / TMEM / tensor-map setup happen once
+//   * lean issue loops: ring stage + phase kept incrementally (no div/mod), UMMA descriptors built
+//     once and advanced by adding to their low word, tap offsets as off0 + tap*step
+//   * TMEM accumulators double-buffered (when 2*n_tile <= 512 columns): the epilogue of tile i
+//     overlaps the MMAs of tile i+1
+//   * epilogue requests its residual / MRF rows BEFORE the accumulator is ready (epilogue.cuh)
+//
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 epilogue.
+#include <cstdlib>
+#include "conv.cuh"
+
+namespace ttsb {
+
+struct ConvTc2Args {
+    int B, T;
+    int tiles_t;       // row tiles per utterance
+    int n_work;        // B * tiles_t
+    int n_tiles_n;
+    int n_chunks, n_taps;
+    int chunk_k;       // 64 or 32
+    int rows_panel;
+    int n_tile, n_sub;
+    int a_slots, b_stages;
+    int acc_bufs;      // 1 or 2
+    int class_split;
+    int shift0[2];     // halo_lo + off(tap 0), per tap class
+    int step[2];       // off(tap+1) - off(tap)
+    int halo_lo;
+    const __half* w;
+    int* err_flag;
+    EpiParams epi;
+};
+
+template <int kTmemCols>
+__global__ void __launch_bounds__(192, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ ConvTc2Args args) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_u32 = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw_u32 & 1023u)) & 1023u);
+
+    const int row_bytes = args.chunk_k * 2;
+    const int panel_bytes = args.rows_panel * row_bytes;
+    const int btile_bytes = args.n_tile * row_bytes;
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + args.a_slots * panel_bytes;
+    uint64_t* full_a = reinterpret_cast<uint64_t*>(smem_b + args.b_stages * btile_bytes);
+    uint64_t* empty_a = full_a + args.a_slots;
+    uint64_t* full_b = empty_a + args.a_slots;
+    uint64_t* empty_b = full_b + args.b_stages;
+    uint64_t* tmem_full = empty_b + args.b_stages;   // [2]
+    uint64_t* tmem_empty = tmem_full + 2;            // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int ntile = blockIdx.x % args.n_tiles_n;
+    const int first = blockIdx.x / args.n_tiles_n;
+    const int stride = gridDim.x / args.n_tiles_n;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        for (int i = 0; i < args.a_slots; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
+        for (int i = 0; i < args.b_stages; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---------------- TMA producer ----------------
+            const uint8_t* wtiles = reinterpret_cast<const uint8_t*>(args.w) +
+                                    static_cast<size_t>(ntile) * args.n_chunks * args.n_taps * btile_bytes;
+            int sa = 0, sb = 0;
+            uint32_t pa = 1, pb = 1;   // parity to wait on the EMPTY barriers (first lap passes)
+            for (int idx = first; idx < args.n_work; idx += stride) {
+                const int b = idx / args.tiles_t;
+                const int row0 = (idx - b * args.tiles_t) * kTileM - args.halo_lo;
+                const uint8_t* wp = wtiles;
+                for (int c = 0; c < args.n_chunks; ++c) {
+                    mbar_wait(&empty_a[sa], pa, args.err_flag, 201);
+                    mbar_expect_tx(&full_a[sa], panel_bytes);
+                    tma_load_3d(smem_a + sa * panel_bytes, &tmap_a, &full_a[sa], c * args.chunk_k, row0, b);
+                    if (++sa == args.a_slots) { sa = 0; pa ^= 1; }
+                    for (int tap = 0; tap < args.n_taps; ++tap) {
+                        mbar_wait(&empty_b[sb], pb, args.err_flag, 202);
+                        mbar_expect_tx(&full_b[sb], btile_bytes);
+                        bulk_load_1d(smem_b + sb * btile_bytes, wp, btile_bytes, &full_b[sb]);
+                        wp += btile_bytes;
+                        if (++sb == args.b_stages) { sb = 0; pb ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---------------- MMA issuer ----------------
+            const int nsub_cols = args.n_tile / args.n_sub;
+            const uint32_t idesc = umma_idesc_f16(kTileM, nsub_cols);
+            const int cls = ntile >= args.class_split ? 1 : 0;
+            const int ksteps = args.chunk_k >> 4;
+            const uint32_t row_u = row_bytes >> 4;                       // descriptor address units (16 B)
+            // descriptor high word: SBO (8-row atom pitch), version 1, swizzle mode
+            const uint32_t desc_hi = ((8u * row_bytes) >> 4) | (1u << 14) | ((row_bytes == 128 ? 2u : 4u) << 29);
+            const uint32_t lo_flag = 1u << 16;                           // LBO field (unused for swizzled K-major)
+            const uint32_t a_lo0 = ((smem_u32(smem_a) & 0x3FFFFu) >> 4) + args.shift0[cls] * row_u;
+            const uint32_t b_lo0 = (smem_u32(smem_b) & 0x3FFFFu) >> 4;
+            const uint32_t panel_u = panel_bytes >> 4, btile_u = btile_bytes >> 4;
+            const uint32_t tap_u = args.step[cls] * row_u;               // may be "negative" (wraps, added mod 2^32)
+            const uint32_t sub_u = (nsub_cols * row_bytes) >> 4;
+            int sa = 0, sb = 0, buf = 0;
+            uint32_t pa = 0, pb = 0;      // parity to wait on the FULL barriers
+            uint32_t pe0 = 1, pe1 = 1;    // parity to wait on tmem_empty[0/1]
+            for (int idx = first; idx < args.n_work; idx += stride) {
+                mbar_wait(&tmem_empty[buf], buf ? pe1 : pe0, args.err_flag, 203);
+                tc_fence_after();
+                if (buf) pe1 ^= 1; else pe0 ^= 1;
+                const uint32_t d_tmem = tmem_base + buf * args.n_tile;
+                uint32_t accumulate = 0;
+                for (int c = 0; c < args.n_chunks; ++c) {
+                    mbar_wait(&full_a[sa], pa, args.err_flag, 204);
+                    uint32_t a_lo = a_lo0 + sa * panel_u;
+                    for (int tap = 0; tap < args.n_taps; ++tap) {
+                        mbar_wait(&full_b[sb], pb, args.err_flag, 205);
+                        tc_fence_after();
+                        const uint32_t b_lo = b_lo0 + sb * btile_u;
+                        for (int s = 0; s < args.n_sub; ++s) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                if (k < ksteps) {
+                                    const uint64_t ad = (static_cast<uint64_t>(desc_hi) << 32) | ((a_lo + 2 * k) & 0x3FFFu) | lo_flag;
+                                    const uint64_t bd = (static_cast<uint64_t>(desc_hi) << 32) | ((b_lo + s * sub_u + 2 * k) & 0x3FFFu) | lo_flag;
+                                    umma_f16(d_tmem + s * nsub_cols, ad, bd, idesc, accumulate | static_cast<uint32_t>(k));
+                                }
+                            }
+                        }
+                        accumulate = 1;
+                        umma_commit(&empty_b[sb]);
+                        if (++sb == args.b_stages) { sb = 0; pb ^= 1; }
+                        a_lo += tap_u;
+                    }
+                    umma_commit(&empty_a[sa]);
+                    if (++sa == args.a_slots) { sa = 0; pa ^= 1; }
+                }
+                umma_commit(&tmem_full[buf]);
+                if (args.acc_bufs == 2) buf ^= 1;
+            }
+        }
+    } else {
+        // ---------------- epilogue: 4 warps x 32 lanes = 128 rows ----------------
+        const int q = warp & 3;
+        int buf = 0;
+        uint32_t pf0 = 0, pf1 = 0;
+        for (int idx = first; idx < args.n_work; idx += stride) {
+            const int b = idx / args.tiles_t;
+            const int t = (idx - b * args.tiles_t) * kTileM + q * 32 + lane;
+            TmemAcc acc{tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * args.n_tile};
+            const uint32_t par = buf ? pf1 : pf0;
+            auto wait_acc = [&] {
+                mbar_wait(&tmem_full[buf], par, args.err_flag, 206);
+                tc_fence_after();
+            };
+            run_epilogue(args.epi, acc, b, t, t < args.T, ntile * args.n_tile, args.n_tile, wait_acc);
+            if (buf) pf1 ^= 1; else pf0 ^= 1;
+            // all TMEM reads of this warp are complete (tcgen05.wait::ld inside acc.load)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+            if (args.acc_bufs == 2) buf ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled2 get_encode_fn2() {
+    static PFN_encodeTiled2 fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled2>(p);
+    }
+    return fn;
+}
+
+static int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <int kCols>
+static int launch_two(const CUtensorMap& tm, const ConvTc2Args& a, int grid, size_t smem, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        TTSB_CHECK_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<kCols>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        configured = true;
+    }
+    conv_tc2_kernel<kCols><<<grid, 192, smem, s>>>(tm, a);
+    count_launch();
+    TTSB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int conv_forward_tc2(const ConvLayer& L, const ConvRuntime& rt, const __half* in, int ld_in, int B,
+                     int T, const EpiParams& epi, cudaStream_t stream) {
+    PFN_encodeTiled2 enc = get_encode_fn2();
+    TTSB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled driver entry point not available");
+    TTSB_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (ld_in % 8) == 0, "input alignment");
+    TTSB_REQUIRE(ld_in >= L.cin, "input row pitch smaller than layer Cin");
+    // tap offsets must be an arithmetic sequence per class (true for conv, transposed conv, linear)
+    int step[2] = {0, 0};
+    for (int c = 0; c < 2; ++c) {
+        step[c] = L.n_taps > 1 ? L.tap_off[c][1] - L.tap_off[c][0] : 0;
+        for (int i = 1; i < L.n_taps; ++i)
+            TTSB_REQUIRE(L.tap_off[c][i] - L.tap_off[c][i - 1] == step[c], "tap offsets must be equally spaced");
+    }
+
+    CUtensorMap tm;
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(L.cin), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(B)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld_in) * 2, static_cast<cuuint64_t>(T) * ld_in * 2};
+    cuuint32_t box[3] = {static_cast<cuuint32_t>(L.chunk_k), static_cast<cuuint32_t>(L.rows_panel), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(in), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     L.chunk_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TTSB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r)));
+
+    ConvTc2Args a;
+    a.B = B; a.T = T;
+    a.tiles_t = ceil_div(T, kTileM);
+    a.n_work = B * a.tiles_t;
+    a.n_tiles_n = L.n_tiles();
+    a.n_chunks = L.n_chunks; a.n_taps = L.n_taps; a.chunk_k = L.chunk_k;
+    a.rows_panel = L.rows_panel;
+    a.n_tile = L.n_tile; a.n_sub = L.n_sub;
+    a.a_slots = L.a_slots2; a.b_stages = L.b_stages2;
+    a.acc_bufs = L.acc_bufs;
+    a.class_split = L.class_split;
+    a.halo_lo = L.halo_lo;
+    for (int c = 0; c < 2; ++c) {
+        a.shift0[c] = L.halo_lo + L.tap_off[c][0];
+        a.step[c] = step[c];
+    }
+    a.w = L.w_packed; a.err_flag = rt.err_flag; a.epi = epi;
+
+    // persistent grid: `occ` CTAs per SM, a multiple of the number of N tiles
+    int ctas = num_sms() * L.occ2;
+    const long total = static_cast<long>(a.n_work) * a.n_tiles_n;
+    if (ctas > total) ctas = static_cast<int>(total);
+    ctas = (ctas / a.n_tiles_n) * a.n_tiles_n;
+    if (ctas < a.n_tiles_n) ctas = a.n_tiles_n;
+    switch (L.tmem_cols2) {
+        case 32: return launch_two<32>(tm, a, ctas, L.smem_bytes2, stream);
+        case 64: return launch_two<64>(tm, a, ctas, L.smem_bytes2, stream);
+        case 128: return launch_two<128>(tm, a, ctas, L.smem_bytes2, stream);
+        case 256: return launch_two<256>(tm, a, ctas, L.smem_bytes2, stream);
+        case 512: return launch_two<512>(tm, a, ctas, L.smem_bytes2, stream);
+    }
+    TTSB_REQUIRE(false, "bad tmem_cols");
+    return 1;
+}
+
+}  // namespace ttsb

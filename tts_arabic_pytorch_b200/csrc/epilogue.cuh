@@ -77,16 +77,52 @@ __device__ __forceinline__ void store8h(__half* p, const float* f) {
     *reinterpret_cast<uint4*>(p) = u;
 }
 
+// Raw 16-byte prefetch of one 32-column chunk of a fp16 row (4 x uint4), issued early so that the
+// global-load latency overlaps the MMA phase / the previous chunk's math.
+struct Chunk32 {
+    uint4 q[4];
+};
+__device__ __forceinline__ void prefetch32(const __half* p, bool on, Chunk32& c) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+        c.q[g] = on ? *(reinterpret_cast<const uint4*>(p) + g) : make_uint4(0, 0, 0, 0);
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    float2 a = unpack_half2(u.x), b = unpack_half2(u.y), c = unpack_half2(u.z), d = unpack_half2(u.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ void bias8(const float* bias, int n, float (&f)[8]) {
+    if (bias == nullptr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = 0.f;
+        return;
+    }
+    const float4 a = __ldg(reinterpret_cast<const float4*>(bias + n));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n) + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
 // b: utterance, t: row inside the utterance, row_ok: t < T (loads from the accumulator are
 // warp-collective, so out-of-range threads still walk the loop but never touch memory).
-// n_base: first logical column of this N tile; n_tile: its width (multiple of 32, or 16).
-template <class Acc>
+// n_base: first logical column of this N tile; n_tile: its width (multiple of 32).
+// `wait_acc()` blocks until the accumulator is complete; it is called AFTER the first chunk of the
+// residual / MRF rows has been requested from HBM.
+template <class Acc, class WaitFn>
 __device__ __forceinline__ void run_epilogue(const EpiParams& e, const Acc& acc, int b, int t,
-                                             bool row_ok, int n_base, int n_tile) {
+                                             bool row_ok, int n_base, int n_tile, WaitFn wait_acc) {
     const long row = static_cast<long>(b) * e.T + t;
     bool in_len = true;
     if (e.lens != nullptr && row_ok) in_len = t < e.lens[b] * e.len_mul;
     const bool do_ln = e.ln_g != nullptr;
+    const __half* res_row = e.residual ? e.residual + row * e.ld_res + n_base : nullptr;
+    const bool use_res = res_row != nullptr && row_ok;
+    const bool use_mrf = e.mrf_mode == MRF_ADD || e.mrf_mode == MRF_LAST;
+    __half* mrf_row = e.mrf_mode != MRF_NONE ? e.mrf_buf + row * e.n_total + n_base : nullptr;
+
+    Chunk32 res_cur, mrf_cur;
+    prefetch32(res_row, use_res, res_cur);
+    prefetch32(mrf_row, use_mrf && row_ok, mrf_cur);
+    wait_acc();
 
     float mean = 0.f, rstd = 1.f;
     if (do_ln) {
@@ -94,17 +130,19 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& e, const Acc& acc,
         float s1 = 0.f, s2 = 0.f;
         for (int c0 = 0; c0 < n_tile; c0 += 32) {
             float v[32];
+            Chunk32 res_nxt;
+            prefetch32(res_row + c0 + 32, use_res && c0 + 32 < n_tile, res_nxt);
             __syncwarp();
             acc.load(c0, v);
             if (row_ok) {
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
-                    const int n = n_base + c0 + g * 8;
-                    float r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                    if (e.residual) load8h(e.residual + row * e.ld_res + n, r);
+                    float r[8], bs[8];
+                    unpack8(res_cur.q[g], r);
+                    bias8(e.bias, n_base + c0 + g * 8, bs);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        float x = v[g * 8 + j] + (e.bias ? __ldg(e.bias + n + j) : 0.f) + r[j];
+                        float x = v[g * 8 + j] + bs[j] + r[j];
                         if (e.pre_ln_relu) x = fmaxf(x, 0.f);
                         v[g * 8 + j] = x;
                         s1 += x;
@@ -114,6 +152,7 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& e, const Acc& acc,
             }
             __syncwarp();
             acc.store(c0, v);
+            res_cur = res_nxt;
         }
         mean = s1 / static_cast<float>(n_tile);
         float var = s2 / static_cast<float>(n_tile) - mean * mean;
@@ -123,62 +162,73 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& e, const Acc& acc,
     float head = 0.f;
     for (int c0 = 0; c0 < n_tile; c0 += 32) {
         float v[32];
+        Chunk32 res_nxt, mrf_nxt;
+        const bool more = c0 + 32 < n_tile;
+        prefetch32(res_row + c0 + 32, use_res && !do_ln && more, res_nxt);
+        prefetch32(mrf_row + c0 + 32, use_mrf && row_ok && more, mrf_nxt);
         __syncwarp();
         acc.load(c0, v);
-        if (!row_ok) continue;
+        if (row_ok) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            if (c0 + g * 8 >= n_tile) break;  // n_tile == 16 case
-            const int n = n_base + c0 + g * 8;
-            float x[8];
-            if (do_ln) {
+            for (int g = 0; g < 4; ++g) {
+                const int n = n_base + c0 + g * 8;
+                float x[8];
+                if (do_ln) {
+                    float gm[8], bt[8];
+                    bias8(e.ln_g, n, gm);
+                    bias8(e.ln_b, n, bt);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    x[j] = (v[g * 8 + j] - mean) * rstd * __ldg(e.ln_g + n + j) + __ldg(e.ln_b + n + j);
-                    if (e.head_w) head += x[j] * __ldg(e.head_w + n + j);
+                    for (int j = 0; j < 8; ++j) x[j] = (v[g * 8 + j] - mean) * rstd * gm[j] + bt[j];
+                    if (e.head_w) {
+                        float hw[8];
+                        bias8(e.head_w, n, hw);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) head += x[j] * hw[j];
+                    }
+                } else {
+                    float r[8], bs[8];
+                    unpack8(res_cur.q[g], r);
+                    bias8(e.bias, n, bs);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) x[j] = v[g * 8 + j] + bs[j] + r[j];
                 }
-            } else {
-                float r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                if (e.residual) load8h(e.residual + row * e.ld_res + n, r);
+                if (e.out_f32_t && e.f32_unmasked) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    x[j] = v[g * 8 + j] + (e.bias ? __ldg(e.bias + n + j) : 0.f) + r[j];
-            }
-            if (e.out_f32_t && e.f32_unmasked) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (n + j < e.n_store)
-                        e.out_f32_t[(static_cast<long>(b) * e.n_store + n + j) * e.T + t] = x[j];
-            }
-            if (!in_len) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) x[j] = 0.f;
-            }
-            if (e.mrf_mode != MRF_NONE) {
-                __half* mb = e.mrf_buf + row * e.n_total + n;
-                float m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                if (e.mrf_mode != MRF_FIRST) load8h(mb, m);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) x[j] = m[j] + x[j] * e.mrf_scale;
-                if (e.mrf_mode != MRF_LAST) {
-                    store8h(mb, x);
-                    continue;
+                    for (int j = 0; j < 8; ++j)
+                        if (n + j < e.n_store)
+                            e.out_f32_t[(static_cast<long>(b) * e.n_store + n + j) * e.T + t] = x[j];
                 }
-            }
-            if (e.out_raw) store8h(e.out_raw + row * e.ld_raw + n, x);
-            if (e.out_f32_t && !e.f32_unmasked) {
+                if (!in_len) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (n + j < e.n_store)
-                        e.out_f32_t[(static_cast<long>(b) * e.n_store + n + j) * e.T + t] = x[j];
-            }
-            if (e.out_act) {
-                float a[8];
+                    for (int j = 0; j < 8; ++j) x[j] = 0.f;
+                }
+                if (e.mrf_mode != MRF_NONE) {
+                    float m[8];
+                    unpack8(mrf_cur.q[g], m);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) a[j] = lrelu(x[j], e.act_slope);
-                store8h(e.out_act + row * e.ld_act + n, a);
+                    for (int j = 0; j < 8; ++j) x[j] = m[j] + x[j] * e.mrf_scale;
+                    if (e.mrf_mode != MRF_LAST) {
+                        store8h(mrf_row + c0 + g * 8, x);
+                        continue;
+                    }
+                }
+                if (e.out_raw) store8h(e.out_raw + row * e.ld_raw + n, x);
+                if (e.out_f32_t && !e.f32_unmasked) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (n + j < e.n_store)
+                            e.out_f32_t[(static_cast<long>(b) * e.n_store + n + j) * e.T + t] = x[j];
+                }
+                if (e.out_act) {
+                    float a[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) a[j] = lrelu(x[j], e.act_slope);
+                    store8h(e.out_act + row * e.ld_act + n, a);
+                }
             }
         }
+        res_cur = res_nxt;
+        mrf_cur = mrf_nxt;
     }
     if (e.head_out && row_ok) e.head_out[row] = in_len ? head + e.head_b : 0.f;
 }

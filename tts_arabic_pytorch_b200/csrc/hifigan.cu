@@ -41,6 +41,7 @@ GlobalRuntime& global_runtime() {
         init = true;
         if (const char* e = getenv("TTSB_CONV_IMPL")) g.impl = (std::string(e) == "simt") ? IMPL_SIMT : IMPL_TC;
         if (const char* e = getenv("TTSB_DESC_MODE")) g.desc_mode = atoi(e);
+        if (const char* e = getenv("TTSB_TC_VERSION")) g.tc_version = atoi(e) == 1 ? 1 : 2;
     }
     return g;
 }
@@ -61,6 +62,7 @@ int get_conv_runtime(size_t simt_elems, ConvRuntime& rt) {
     }
     rt.impl = g.impl;
     rt.desc_mode = g.desc_mode;
+    rt.tc_version = g.desc_mode != 0 ? 1 : g.tc_version;   // descriptor probes exist only in v1
     rt.err_flag = g.err_flag;
     rt.simt_scratch = g.simt_scratch;
     rt.simt_scratch_elems = g.simt_scratch_elems;

@@ -12,6 +12,7 @@ namespace ttsb {
 
 struct GlobalRuntime {
     int impl = IMPL_TC;
+    int tc_version = 2;
     int desc_mode = 0;  // verified on B200 (profiles/r01_s1_probe_conv.json): base_offset stays 0
     int* err_flag = nullptr;
     float* simt_scratch = nullptr;
