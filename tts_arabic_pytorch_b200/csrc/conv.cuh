@@ -37,6 +37,8 @@ struct ConvLayer {
     size_t smem_bytes = 0;
     // persistent kernel (conv_tc2) plan
     int a_slots2 = 0, b_stages2 = 0, acc_bufs = 1, occ2 = 1, tmem_cols2 = 0;
+    int rpp = 1;        // row tiles per weight pass
+    int resident = 0;   // weights stay in smem
     size_t smem_bytes2 = 0;
     // device data
     __half* w_packed = nullptr;  // [n_tiles][chunk][tap] tiles of n_tile x chunk_k, pre-swizzled

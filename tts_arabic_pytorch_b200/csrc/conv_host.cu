@@ -84,28 +84,56 @@ int conv_layer_create(ConvLayer& L, int cin_logical, int cin_stored, int n_total
     L.b_stages = b_stages;
     L.smem_bytes = 1024 + a_slots * panel + b_stages * btile + (2 * a_slots + 2 * b_stages + 1) * 8 + 16;
 
-    // persistent-kernel plan: two CTAs per SM for light tiles (HBM-bound stages), one CTA with deep
-    // rings otherwise; accumulators double-buffered in TMEM when two tiles fit in 512 columns
+    // persistent-kernel plan (conv_tc2).
+    //  * resident: every weight tile of an N tile fits in smem next to >= 2 tiles' worth of
+    //    activation panels -> loaded once per CTA, the per-tile work is A panels + MMAs + epilogue
+    //  * streamed: weights re-streamed from L2 per work item; rpp row tiles share one pass so the
+    //    L2->SM weight traffic per output row drops by rpp (v2 microbench: C=128/256 k>=7 layers were
+    //    bound by ~5.5 TB/s of weight re-streaming)
+    //  * accumulators double-buffered in TMEM when two work items fit in 512 columns
     {
-        L.acc_bufs = 2 * n_tile <= 512 ? 2 : 1;
-        L.tmem_cols2 = 32;
-        while (L.tmem_cols2 < L.acc_bufs * n_tile) L.tmem_cols2 *= 2;
         const size_t full = kSmemMax - 2048;
-        const size_t half = 110 * 1024;
         const int total_b = L.n_chunks * n_taps;
-        const bool light = L.n_chunks * panel + std::min(4, total_b) * btile <= half && L.tmem_cols2 <= 256;
-        L.occ2 = light ? 2 : 1;
-        if (const char* e = getenv("TTSB_OCC2")) L.occ2 = std::max(1, std::min(atoi(e), light ? 4 : 1));
-        const size_t bud = std::min(budget, L.occ2 >= 2 ? (kSmemMax / L.occ2 - 3072) : full);
-        int as2 = L.n_chunks;
-        if (as2 * panel + 2 * btile > bud) as2 = std::min(L.n_chunks, 2);
-        if (2 * L.n_chunks * panel + std::min(4, total_b) * btile <= bud) as2 = 2 * L.n_chunks;
-        int bs2 = static_cast<int>((bud - as2 * panel) / btile);
-        bs2 = std::min(bs2, std::min(std::max(max_b, 8), total_b));
-        TTSB_REQUIRE(bs2 >= 1 && as2 >= 1, "persistent tile does not fit in shared memory");
-        L.a_slots2 = as2;
-        L.b_stages2 = bs2;
-        L.smem_bytes2 = 1024 + as2 * panel + bs2 * btile + (2 * as2 + 2 * bs2 + 4) * 8 + 16;
+        const size_t bar_bytes = 1024 + 4096;
+        const size_t w_all = static_cast<size_t>(total_b) * btile;
+        int want_res = w_all + 2 * L.n_chunks * panel + bar_bytes <= full ? 1 : 0;
+        if (const char* e = getenv("TTSB_RESIDENT")) want_res = want_res && atoi(e) != 0;
+        L.resident = want_res;
+        int rpp = 1;
+        if (!L.resident) rpp = n_tile <= 256 ? 2 : 1;
+        if (const char* e = getenv("TTSB_RPP")) {
+            const int v = atoi(e);
+            if (!L.resident && (v == 1 || v == 2 || v == 4) && v * n_tile <= 512) rpp = v;
+        }
+        L.rpp = rpp;
+        L.acc_bufs = 2 * rpp * n_tile <= 512 ? 2 : 1;
+        L.tmem_cols2 = 32;
+        while (L.tmem_cols2 < L.acc_bufs * rpp * n_tile) L.tmem_cols2 *= 2;
+        if (L.resident) {
+            const size_t half = kSmemMax / 2 - 3072;
+            const bool light = w_all + 2 * L.n_chunks * panel + bar_bytes <= half && L.tmem_cols2 <= 256;
+            L.occ2 = light ? 2 : 1;
+            if (const char* e = getenv("TTSB_OCC2")) L.occ2 = std::max(1, std::min(atoi(e), light ? 2 : 1));
+            const size_t bud = std::min(budget, L.occ2 == 2 ? half : full) - w_all - bar_bytes;
+            int as2 = static_cast<int>(bud / panel);
+            as2 = std::min(as2, 4 * L.n_chunks);
+            TTSB_REQUIRE(as2 >= 1, "resident plan does not fit");
+            L.a_slots2 = as2;
+            L.b_stages2 = 1;
+            L.smem_bytes2 = 1024 + as2 * panel + w_all + (2 * as2 + 2 + 5) * 8 + 16;
+        } else {
+            L.occ2 = 1;
+            const size_t bud = std::min(budget, full) - bar_bytes;
+            int as2 = rpp * L.n_chunks;                                  // a whole work item resident
+            if (as2 * panel + 3 * btile > bud) as2 = std::min(rpp * L.n_chunks, 2 * rpp);   // two chunks in flight
+            if (as2 * panel + 2 * btile > bud) as2 = rpp;
+            int bs2 = static_cast<int>((bud - as2 * panel) / btile);
+            bs2 = std::min(bs2, std::min(std::max(max_b, 8), total_b));
+            TTSB_REQUIRE(bs2 >= 2 && as2 >= rpp, "persistent tile does not fit in shared memory");
+            L.a_slots2 = as2;
+            L.b_stages2 = bs2;
+            L.smem_bytes2 = 1024 + as2 * panel + bs2 * btile + (2 * as2 + 2 * bs2 + 5) * 8 + 16;
+        }
     }
 
     // pack weights: [n_tiles][chunk][tap] tiles, fp16, swizzled

@@ -23,7 +23,10 @@ namespace ttsb {
 struct ConvTc2Args {
     int B, T;
     int tiles_t;       // row tiles per utterance
-    int n_work;        // B * tiles_t
+    int rpp;           // row tiles per weight pass (1, 2 or 4): one work item = rpp consecutive tiles
+    int groups_t;      // work items per utterance = ceil(tiles_t / rpp)
+    int n_work;        // B * groups_t
+    int resident;      // 1: all weight tiles of this N tile stay in smem for the CTA's lifetime
     int n_tiles_n;
     int n_chunks, n_taps;
     int chunk_k;       // 64 or 32
@@ -52,13 +55,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const int btile_bytes = args.n_tile * row_bytes;
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + args.a_slots * panel_bytes;
-    uint64_t* full_a = reinterpret_cast<uint64_t*>(smem_b + args.b_stages * btile_bytes);
+    const int n_btiles = args.n_chunks * args.n_taps;
+    const int b_slots = args.resident ? n_btiles : args.b_stages;
+    uint64_t* full_a = reinterpret_cast<uint64_t*>(smem_b + b_slots * btile_bytes);
     uint64_t* empty_a = full_a + args.a_slots;
     uint64_t* full_b = empty_a + args.a_slots;
     uint64_t* empty_b = full_b + args.b_stages;
     uint64_t* tmem_full = empty_b + args.b_stages;   // [2]
     uint64_t* tmem_empty = tmem_full + 2;            // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* w_full = tmem_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -71,6 +77,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         for (int i = 0; i < args.a_slots; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
         for (int i = 0; i < args.b_stages; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+        mbar_init(w_full, 1);
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
@@ -86,21 +93,31 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                                     static_cast<size_t>(ntile) * args.n_chunks * args.n_taps * btile_bytes;
             int sa = 0, sb = 0;
             uint32_t pa = 1, pb = 1;   // parity to wait on the EMPTY barriers (first lap passes)
+            if (args.resident) {
+                mbar_expect_tx(w_full, n_btiles * btile_bytes);
+                for (int i = 0; i < n_btiles; ++i)
+                    bulk_load_1d(smem_b + i * btile_bytes, wtiles + static_cast<size_t>(i) * btile_bytes, btile_bytes, w_full);
+            }
             for (int idx = first; idx < args.n_work; idx += stride) {
-                const int b = idx / args.tiles_t;
-                const int row0 = (idx - b * args.tiles_t) * kTileM - args.halo_lo;
+                const int b = idx / args.groups_t;
+                const int tile0 = (idx - b * args.groups_t) * args.rpp;
                 const uint8_t* wp = wtiles;
                 for (int c = 0; c < args.n_chunks; ++c) {
-                    mbar_wait(&empty_a[sa], pa, args.err_flag, 201);
-                    mbar_expect_tx(&full_a[sa], panel_bytes);
-                    tma_load_3d(smem_a + sa * panel_bytes, &tmap_a, &full_a[sa], c * args.chunk_k, row0, b);
-                    if (++sa == args.a_slots) { sa = 0; pa ^= 1; }
-                    for (int tap = 0; tap < args.n_taps; ++tap) {
-                        mbar_wait(&empty_b[sb], pb, args.err_flag, 202);
-                        mbar_expect_tx(&full_b[sb], btile_bytes);
-                        bulk_load_1d(smem_b + sb * btile_bytes, wp, btile_bytes, &full_b[sb]);
-                        wp += btile_bytes;
-                        if (++sb == args.b_stages) { sb = 0; pb ^= 1; }
+                    for (int r = 0; r < args.rpp; ++r) {
+                        mbar_wait(&empty_a[sa], pa, args.err_flag, 201);
+                        mbar_expect_tx(&full_a[sa], panel_bytes);
+                        tma_load_3d(smem_a + sa * panel_bytes, &tmap_a, &full_a[sa], c * args.chunk_k,
+                                    (tile0 + r) * kTileM - args.halo_lo, b);
+                        if (++sa == args.a_slots) { sa = 0; pa ^= 1; }
+                    }
+                    if (!args.resident) {
+                        for (int tap = 0; tap < args.n_taps; ++tap) {
+                            mbar_wait(&empty_b[sb], pb, args.err_flag, 202);
+                            mbar_expect_tx(&full_b[sb], btile_bytes);
+                            bulk_load_1d(smem_b + sb * btile_bytes, wp, btile_bytes, &full_b[sb]);
+                            wp += btile_bytes;
+                            if (++sb == args.b_stages) { sb = 0; pb ^= 1; }
+                        }
                     }
                 }
             }
@@ -124,36 +141,65 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             int sa = 0, sb = 0, buf = 0;
             uint32_t pa = 0, pb = 0;      // parity to wait on the FULL barriers
             uint32_t pe0 = 1, pe1 = 1;    // parity to wait on tmem_empty[0/1]
+            const int buf_cols = args.rpp * args.n_tile;
+            if (args.resident) {
+                mbar_wait(w_full, 0, args.err_flag, 207);
+                tc_fence_after();
+            }
             for (int idx = first; idx < args.n_work; idx += stride) {
                 mbar_wait(&tmem_empty[buf], buf ? pe1 : pe0, args.err_flag, 203);
                 tc_fence_after();
                 if (buf) pe1 ^= 1; else pe0 ^= 1;
-                const uint32_t d_tmem = tmem_base + buf * args.n_tile;
+                const uint32_t d_tmem = tmem_base + buf * buf_cols;
                 uint32_t accumulate = 0;
                 for (int c = 0; c < args.n_chunks; ++c) {
-                    mbar_wait(&full_a[sa], pa, args.err_flag, 204);
-                    uint32_t a_lo = a_lo0 + sa * panel_u;
-                    for (int tap = 0; tap < args.n_taps; ++tap) {
-                        mbar_wait(&full_b[sb], pb, args.err_flag, 205);
-                        tc_fence_after();
-                        const uint32_t b_lo = b_lo0 + sb * btile_u;
-                        for (int s = 0; s < args.n_sub; ++s) {
+                    uint32_t a_lo[4];
+                    int a_slot[4];
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                if (k < ksteps) {
-                                    const uint64_t ad = (static_cast<uint64_t>(desc_hi) << 32) | ((a_lo + 2 * k) & 0x3FFFu) | lo_flag;
-                                    const uint64_t bd = (static_cast<uint64_t>(desc_hi) << 32) | ((b_lo + s * sub_u + 2 * k) & 0x3FFFu) | lo_flag;
-                                    umma_f16(d_tmem + s * nsub_cols, ad, bd, idesc, accumulate | static_cast<uint32_t>(k));
+                    for (int r = 0; r < 4; ++r) {
+                        if (r < args.rpp) {
+                            mbar_wait(&full_a[sa], pa, args.err_flag, 204);
+                            a_lo[r] = a_lo0 + sa * panel_u;
+                            a_slot[r] = sa;
+                            if (++sa == args.a_slots) { sa = 0; pa ^= 1; }
+                        }
+                    }
+                    tc_fence_after();
+                    for (int tap = 0; tap < args.n_taps; ++tap) {
+                        uint32_t b_lo;
+                        if (args.resident) {
+                            b_lo = b_lo0 + (c * args.n_taps + tap) * btile_u;
+                        } else {
+                            mbar_wait(&full_b[sb], pb, args.err_flag, 205);
+                            tc_fence_after();
+                            b_lo = b_lo0 + sb * btile_u;
+                        }
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            if (r < args.rpp) {
+                                for (int s = 0; s < args.n_sub; ++s) {
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        if (k < ksteps) {
+                                            const uint64_t ad = (static_cast<uint64_t>(desc_hi) << 32) | ((a_lo[r] + 2 * k) & 0x3FFFu) | lo_flag;
+                                            const uint64_t bd = (static_cast<uint64_t>(desc_hi) << 32) | ((b_lo + s * sub_u + 2 * k) & 0x3FFFu) | lo_flag;
+                                            umma_f16(d_tmem + r * args.n_tile + s * nsub_cols, ad, bd, idesc,
+                                                     accumulate | static_cast<uint32_t>(k));
+                                        }
+                                    }
                                 }
+                                a_lo[r] += tap_u;
                             }
                         }
                         accumulate = 1;
-                        umma_commit(&empty_b[sb]);
-                        if (++sb == args.b_stages) { sb = 0; pb ^= 1; }
-                        a_lo += tap_u;
+                        if (!args.resident) {
+                            umma_commit(&empty_b[sb]);
+                            if (++sb == args.b_stages) { sb = 0; pb ^= 1; }
+                        }
                     }
-                    umma_commit(&empty_a[sa]);
-                    if (++sa == args.a_slots) { sa = 0; pa ^= 1; }
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        if (r < args.rpp) umma_commit(&empty_a[a_slot[r]]);
                 }
                 umma_commit(&tmem_full[buf]);
                 if (args.acc_bufs == 2) buf ^= 1;
@@ -164,16 +210,22 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         const int q = warp & 3;
         int buf = 0;
         uint32_t pf0 = 0, pf1 = 0;
+        const int buf_cols = args.rpp * args.n_tile;
         for (int idx = first; idx < args.n_work; idx += stride) {
-            const int b = idx / args.tiles_t;
-            const int t = (idx - b * args.tiles_t) * kTileM + q * 32 + lane;
-            TmemAcc acc{tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * args.n_tile};
+            const int b = idx / args.groups_t;
+            const int tile0 = (idx - b * args.groups_t) * args.rpp;
             const uint32_t par = buf ? pf1 : pf0;
-            auto wait_acc = [&] {
-                mbar_wait(&tmem_full[buf], par, args.err_flag, 206);
-                tc_fence_after();
-            };
-            run_epilogue(args.epi, acc, b, t, t < args.T, ntile * args.n_tile, args.n_tile, wait_acc);
+            for (int r = 0; r < args.rpp; ++r) {
+                const int t = (tile0 + r) * kTileM + q * 32 + lane;
+                TmemAcc acc{tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * buf_cols + r * args.n_tile};
+                auto wait_acc = [&] {
+                    if (r == 0) {
+                        mbar_wait(&tmem_full[buf], par, args.err_flag, 206);
+                        tc_fence_after();
+                    }
+                };
+                run_epilogue(args.epi, acc, b, t, t < args.T, ntile * args.n_tile, args.n_tile, wait_acc);
+            }
             if (buf) pf1 ^= 1; else pf0 ^= 1;
             // all TMEM reads of this warp are complete (tcgen05.wait::ld inside acc.load)
             tc_fence_before();
@@ -260,7 +312,10 @@ int conv_forward_tc2(const ConvLayer& L, const ConvRuntime& rt, const __half* in
     ConvTc2Args a;
     a.B = B; a.T = T;
     a.tiles_t = ceil_div(T, kTileM);
-    a.n_work = B * a.tiles_t;
+    a.rpp = L.rpp;
+    a.groups_t = ceil_div(a.tiles_t, a.rpp);
+    a.n_work = B * a.groups_t;
+    a.resident = L.resident;
     a.n_tiles_n = L.n_tiles();
     a.n_chunks = L.n_chunks; a.n_taps = L.n_taps; a.chunk_k = L.chunk_k;
     a.rows_panel = L.rows_panel;
