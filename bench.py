@@ -192,6 +192,15 @@ def run_ours(args):
     samples_per_step = B * T * HOP
 
     voc_ms = []
+    # N > 1: the only collective of the path — deliver every rank's waveforms to rank 0 over NCCL
+    gather_bufs = None
+    if world > 1 and rank == 0:
+        gather_bufs = [torch.empty(B, T * HOP, dtype=torch.float32, device=dev) for _ in range(world)]
+
+    def deliver(wav):
+        if world > 1:
+            dist.gather(wav, gather_bufs, dst=0)
+        return wav
 
     def step_device():
         mel, dec_lens, _, _, _, mel_cl = fp.infer(ids_dev, return_channel_last=True)
@@ -201,12 +210,12 @@ def run_ours(args):
         wav = voc.run(mel_cl=mel_cl, lens=dec_lens)
         e1.record()
         voc_ms.append((e0, e1))
-        return wav
+        return deliver(wav)
 
     def step_e2e():
         ids = ids_host.to(dev, non_blocking=True)
         mel, dec_lens, _, _, _, mel_cl = fp.infer(ids, return_channel_last=True)
-        wav = voc.run(mel_cl=mel_cl, lens=dec_lens)
+        wav = deliver(voc.run(mel_cl=mel_cl, lens=dec_lens))
         wav_host.copy_(wav, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return wav

@@ -84,23 +84,28 @@ int conv_layer_create(ConvLayer& L, int cin_logical, int cin_stored, int n_total
     L.b_stages = b_stages;
     L.smem_bytes = 1024 + a_slots * panel + b_stages * btile + (2 * a_slots + 2 * b_stages + 1) * 8 + 16;
 
-    // persistent-kernel plan (conv_tc2).
-    //  * resident: every weight tile of an N tile fits in smem next to >= 2 tiles' worth of
-    //    activation panels -> loaded once per CTA, the per-tile work is A panels + MMAs + epilogue
-    //  * streamed: weights re-streamed from L2 per work item; rpp row tiles share one pass so the
-    //    L2->SM weight traffic per output row drops by rpp (v2 microbench: C=128/256 k>=7 layers were
-    //    bound by ~5.5 TB/s of weight re-streaming)
-    //  * accumulators double-buffered in TMEM when two work items fit in 512 columns
+    // persistent-kernel plan (conv_tc2). Measured on B200 (profiles/r01_s4, r01_s5):
+    //  * light tiles (everything fits in half the SM's smem): TWO CTAs per SM beat any single-CTA
+    //    variant — the per-tile chain wait->tcgen05.ld->global loads->stores is latency-bound
+    //  * heavy tiles (C >= 128 with k >= 7, C = 256): one CTA per SM; the weight stream from L2
+    //    (~5.5 TB/s aggregate) is the limiter, so rpp row tiles share one weight pass
+    //  * resident weights (loaded once per CTA) are used when they fit next to the panel ring
+    //  * the A-panel ring always has room to prefetch the next work item's first chunk
     {
         const size_t full = kSmemMax - 2048;
+        const size_t half = kSmemMax / 2 - 3072;
         const int total_b = L.n_chunks * n_taps;
-        const size_t bar_bytes = 1024 + 4096;
+        const size_t bar_bytes = 1024 + 2048;
         const size_t w_all = static_cast<size_t>(total_b) * btile;
-        int want_res = w_all + 2 * L.n_chunks * panel + bar_bytes <= full ? 1 : 0;
+        const bool light = L.n_chunks * panel + std::min(4, total_b) * btile + bar_bytes <= half && 2 * n_tile <= 256;
+        L.occ2 = light ? 2 : 1;
+        if (const char* e = getenv("TTSB_OCC2")) L.occ2 = std::max(1, std::min(atoi(e), light ? 2 : 1));
+        const size_t bud = std::min(budget, L.occ2 == 2 ? half : full) - bar_bytes;
+        int want_res = w_all + (L.n_chunks + 1) * panel <= bud ? 1 : 0;
         if (const char* e = getenv("TTSB_RESIDENT")) want_res = want_res && atoi(e) != 0;
         L.resident = want_res;
         int rpp = 1;
-        if (!L.resident) rpp = n_tile <= 256 ? 2 : 1;
+        if (!L.resident && L.occ2 == 1) rpp = n_tile <= 256 ? 2 : 1;
         if (const char* e = getenv("TTSB_RPP")) {
             const int v = atoi(e);
             if (!L.resident && (v == 1 || v == 2 || v == 4) && v * n_tile <= 512) rpp = v;
@@ -110,22 +115,18 @@ int conv_layer_create(ConvLayer& L, int cin_logical, int cin_stored, int n_total
         L.tmem_cols2 = 32;
         while (L.tmem_cols2 < L.acc_bufs * rpp * n_tile) L.tmem_cols2 *= 2;
         if (L.resident) {
-            const size_t half = kSmemMax / 2 - 3072;
-            const bool light = w_all + 2 * L.n_chunks * panel + bar_bytes <= half && L.tmem_cols2 <= 256;
-            L.occ2 = light ? 2 : 1;
-            if (const char* e = getenv("TTSB_OCC2")) L.occ2 = std::max(1, std::min(atoi(e), light ? 2 : 1));
-            const size_t bud = std::min(budget, L.occ2 == 2 ? half : full) - w_all - bar_bytes;
-            int as2 = static_cast<int>(bud / panel);
+            int as2 = static_cast<int>((bud - w_all) / panel);
             as2 = std::min(as2, 4 * L.n_chunks);
-            TTSB_REQUIRE(as2 >= 1, "resident plan does not fit");
             L.a_slots2 = as2;
             L.b_stages2 = 1;
             L.smem_bytes2 = 1024 + as2 * panel + w_all + (2 * as2 + 2 + 5) * 8 + 16;
         } else {
-            L.occ2 = 1;
-            const size_t bud = std::min(budget, full) - bar_bytes;
-            int as2 = rpp * L.n_chunks;                                  // a whole work item resident
-            if (as2 * panel + 3 * btile > bud) as2 = std::min(rpp * L.n_chunks, 2 * rpp);   // two chunks in flight
+            const int item = rpp * L.n_chunks;                 // panels of one work item
+            int as2 = 2 * item;                                // two work items in flight
+            const int min_b = std::min(4, total_b);
+            if (as2 * panel + min_b * btile > bud) as2 = item + rpp;      // + the next item's first chunk
+            if (as2 * panel + min_b * btile > bud) as2 = 3 * rpp;         // three chunks in flight
+            if (as2 * panel + 2 * btile > bud) as2 = 2 * rpp;
             if (as2 * panel + 2 * btile > bud) as2 = rpp;
             int bs2 = static_cast<int>((bud - as2 * panel) / btile);
             bs2 = std::min(bs2, std::min(std::max(max_b, 8), total_b));
