@@ -84,34 +84,33 @@ int conv_layer_create(ConvLayer& L, int cin_logical, int cin_stored, int n_total
     L.b_stages = b_stages;
     L.smem_bytes = 1024 + a_slots * panel + b_stages * btile + (2 * a_slots + 2 * b_stages + 1) * 8 + 16;
 
-    // persistent-kernel plan (conv_tc2). Measured on B200 (profiles/r01_s4, r01_s5):
-    //  * light tiles (everything fits in half the SM's smem): TWO CTAs per SM beat any single-CTA
-    //    variant — the per-tile chain wait->tcgen05.ld->global loads->stores is latency-bound
-    //  * heavy tiles (C >= 128 with k >= 7, C = 256): one CTA per SM; the weight stream from L2
-    //    (~5.5 TB/s aggregate) is the limiter, so rpp row tiles share one weight pass
-    //  * resident weights (loaded once per CTA) are used when they fit next to the panel ring
-    //  * the A-panel ring always has room to prefetch the next work item's first chunk
+    // persistent-kernel plan (conv_tc2). Measured on B200 (profiles/r01_s4..s6):
+    //  * TWO CTAs per SM beat one whenever a (reduced) configuration fits in half the smem and
+    //    half the TMEM: two independent producer/MMA/epilogue pipelines hide each other's bubbles
+    //  * weights stay resident in smem when they fit next to the panel ring
+    //  * rpp > 1 (several row tiles per weight pass) only by request (TTSB_RPP), see DESIGN.md
     {
         const size_t full = kSmemMax - 2048;
-        const size_t half = kSmemMax / 2 - 3072;
+        const size_t half = kSmemMax / 2 - 2048;
         const int total_b = L.n_chunks * n_taps;
-        const size_t bar_bytes = 1024 + 2048;
+        const size_t bar_bytes = 1024 + 1024;
         const size_t w_all = static_cast<size_t>(total_b) * btile;
-        const bool light = L.n_chunks * panel + std::min(4, total_b) * btile + bar_bytes <= half && 2 * n_tile <= 256;
-        L.occ2 = light ? 2 : 1;
-        if (const char* e = getenv("TTSB_OCC2")) L.occ2 = std::max(1, std::min(atoi(e), light ? 2 : 1));
+        const int min_a = std::min(L.n_chunks, 2);
+        const bool can2 = min_a * panel + 2 * btile + bar_bytes <= half && n_tile <= 256;
+        L.occ2 = can2 ? 2 : 1;
+        if (const char* e = getenv("TTSB_OCC2")) L.occ2 = std::max(1, std::min(atoi(e), can2 ? 2 : 1));
         const size_t bud = std::min(budget, L.occ2 == 2 ? half : full) - bar_bytes;
-        int want_res = w_all + (L.n_chunks + 1) * panel <= bud ? 1 : 0;
+        int want_res = w_all + std::min(L.n_chunks + 1, 2 * L.n_chunks) * panel <= bud ? 1 : 0;
         if (const char* e = getenv("TTSB_RESIDENT")) want_res = want_res && atoi(e) != 0;
         L.resident = want_res;
         int rpp = 1;
-        if (!L.resident && L.occ2 == 1) rpp = n_tile <= 256 ? 2 : 1;
         if (const char* e = getenv("TTSB_RPP")) {
             const int v = atoi(e);
-            if (!L.resident && (v == 1 || v == 2 || v == 4) && v * n_tile <= 512) rpp = v;
+            if (!L.resident && L.occ2 == 1 && (v == 1 || v == 2 || v == 4) && v * n_tile <= 512) rpp = v;
         }
         L.rpp = rpp;
-        L.acc_bufs = 2 * rpp * n_tile <= 512 ? 2 : 1;
+        const int tmem_cap = L.occ2 == 2 ? 256 : 512;
+        L.acc_bufs = 2 * rpp * n_tile <= tmem_cap ? 2 : 1;
         L.tmem_cols2 = 32;
         while (L.tmem_cols2 < L.acc_bufs * rpp * n_tile) L.tmem_cols2 *= 2;
         if (L.resident) {
@@ -122,11 +121,12 @@ int conv_layer_create(ConvLayer& L, int cin_logical, int cin_stored, int n_total
             L.smem_bytes2 = 1024 + as2 * panel + w_all + (2 * as2 + 2 + 5) * 8 + 16;
         } else {
             const int item = rpp * L.n_chunks;                 // panels of one work item
+            const int min_b = std::min(L.occ2 == 2 ? 3 : 4, total_b);
             int as2 = 2 * item;                                // two work items in flight
-            const int min_b = std::min(4, total_b);
             if (as2 * panel + min_b * btile > bud) as2 = item + rpp;      // + the next item's first chunk
-            if (as2 * panel + min_b * btile > bud) as2 = 3 * rpp;         // three chunks in flight
-            if (as2 * panel + 2 * btile > bud) as2 = 2 * rpp;
+            if (as2 * panel + min_b * btile > bud) as2 = item;
+            if (as2 * panel + 2 * btile > bud) as2 = std::min(item, 3 * rpp);
+            if (as2 * panel + 2 * btile > bud) as2 = std::min(item, 2 * rpp);
             if (as2 * panel + 2 * btile > bud) as2 = rpp;
             int bs2 = static_cast<int>((bud - as2 * panel) / btile);
             bs2 = std::min(bs2, std::min(std::max(max_b, 8), total_b));

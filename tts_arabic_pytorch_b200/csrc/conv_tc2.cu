@@ -87,39 +87,49 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ---------------- TMA producer ----------------
-            const uint8_t* wtiles = reinterpret_cast<const uint8_t*>(args.w) +
-                                    static_cast<size_t>(ntile) * args.n_chunks * args.n_taps * btile_bytes;
-            int sa = 0, sb = 0;
-            uint32_t pa = 1, pb = 1;   // parity to wait on the EMPTY barriers (first lap passes)
+        // ---------------- TMA producers ----------------
+        // Issuing one TMA costs the issuing thread ~500 cycles of dependent mbarrier/UBLKCP latency
+        // (v1 timeline), more than the MMA time of a 16 KB weight tile. The loads are therefore
+        // spread over lanes: lanes 0..7 own weight-tile loads j = lane, lane+8, ..., lanes 8..11 own
+        // activation panels p = lane-8, lane-4, ... Ring slot and phase follow from the load index,
+        // so the lanes never have to agree on anything.
+        const int n_items = first < args.n_work ? (args.n_work - first + stride - 1) / stride : 0;
+        const uint8_t* wtiles = reinterpret_cast<const uint8_t*>(args.w) +
+                                static_cast<size_t>(ntile) * n_btiles * btile_bytes;
+        if (lane < 8) {
             if (args.resident) {
-                mbar_expect_tx(w_full, n_btiles * btile_bytes);
-                for (int i = 0; i < n_btiles; ++i)
+                if (lane == 0) mbar_expect_tx(w_full, n_btiles * btile_bytes);
+                __syncwarp(0xFFu);
+                for (int i = lane; i < n_btiles; i += 8)
                     bulk_load_1d(smem_b + i * btile_bytes, wtiles + static_cast<size_t>(i) * btile_bytes, btile_bytes, w_full);
+            } else {
+                const uint32_t total = static_cast<uint32_t>(n_items) * n_btiles;
+                for (uint32_t j = lane; j < total; j += 8) {
+                    const int q = static_cast<int>(j % static_cast<uint32_t>(n_btiles));
+                    const uint32_t lap = j / static_cast<uint32_t>(args.b_stages);
+                    const int sb = static_cast<int>(j - lap * args.b_stages);
+                    mbar_wait(&empty_b[sb], (lap & 1u) ^ 1u, args.err_flag, 202);
+                    mbar_expect_tx(&full_b[sb], btile_bytes);
+                    bulk_load_1d(smem_b + sb * btile_bytes, wtiles + static_cast<size_t>(q) * btile_bytes, btile_bytes,
+                                 &full_b[sb]);
+                }
             }
-            for (int idx = first; idx < args.n_work; idx += stride) {
+        } else if (lane < 12) {
+            const int per_item = args.n_chunks * args.rpp;
+            const uint32_t total = static_cast<uint32_t>(n_items) * per_item;
+            for (uint32_t p = lane - 8; p < total; p += 4) {
+                const int item = static_cast<int>(p / static_cast<uint32_t>(per_item));
+                const int rem = static_cast<int>(p - static_cast<uint32_t>(item) * per_item);
+                const int c = rem / args.rpp, r = rem - c * args.rpp;
+                const int idx = first + item * stride;
                 const int b = idx / args.groups_t;
                 const int tile0 = (idx - b * args.groups_t) * args.rpp;
-                const uint8_t* wp = wtiles;
-                for (int c = 0; c < args.n_chunks; ++c) {
-                    for (int r = 0; r < args.rpp; ++r) {
-                        mbar_wait(&empty_a[sa], pa, args.err_flag, 201);
-                        mbar_expect_tx(&full_a[sa], panel_bytes);
-                        tma_load_3d(smem_a + sa * panel_bytes, &tmap_a, &full_a[sa], c * args.chunk_k,
-                                    (tile0 + r) * kTileM - args.halo_lo, b);
-                        if (++sa == args.a_slots) { sa = 0; pa ^= 1; }
-                    }
-                    if (!args.resident) {
-                        for (int tap = 0; tap < args.n_taps; ++tap) {
-                            mbar_wait(&empty_b[sb], pb, args.err_flag, 202);
-                            mbar_expect_tx(&full_b[sb], btile_bytes);
-                            bulk_load_1d(smem_b + sb * btile_bytes, wp, btile_bytes, &full_b[sb]);
-                            wp += btile_bytes;
-                            if (++sb == args.b_stages) { sb = 0; pb ^= 1; }
-                        }
-                    }
-                }
+                const uint32_t lap = p / static_cast<uint32_t>(args.a_slots);
+                const int sa = static_cast<int>(p - lap * args.a_slots);
+                mbar_wait(&empty_a[sa], (lap & 1u) ^ 1u, args.err_flag, 201);
+                mbar_expect_tx(&full_a[sa], panel_bytes);
+                tma_load_3d(smem_a + sa * panel_bytes, &tmap_a, &full_a[sa], c * args.chunk_k,
+                            (tile0 + r) * kTileM - args.halo_lo, b);
             }
         }
     } else if (warp == 1) {

@@ -21,7 +21,7 @@ struct ttsb_hifigan {
     ttsb_hifigan_config_t cfg;
     int device = 0;
     int hop = 1;
-    int chunk_frames = 2048;
+    int chunk_frames = 32768;   // frames per pass through the generator (workspace ~ 128 KB per frame)
     ConvLayer conv_pre;
     std::vector<ConvLayer> ups;
     std::vector<ConvLayer> c1, c2;  // index ((stage*num_kernels)+j)*3+p
