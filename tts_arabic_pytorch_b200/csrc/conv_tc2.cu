@@ -16,6 +16,8 @@
 //
 // Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 epilogue.
 #include <cstdlib>
+#include <utility>
+#include <vector>
 #include "conv.cuh"
 
 namespace ttsb {
@@ -34,6 +36,7 @@ struct ConvTc2Args {
     int n_tile, n_sub;
     int a_slots, b_stages;
     int acc_bufs;      // 1 or 2
+    int a_lanes, b_lanes;   // producer lanes; each divides its ring size so a ring slot is always served by the same lane
     int class_split;
     int shift0[2];     // halo_lo + off(tap 0), per tap class
     int step[2];       // off(tap+1) - off(tap)
@@ -90,9 +93,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         // ---------------- TMA producers ----------------
         // Issuing one TMA costs the issuing thread ~500 cycles of dependent mbarrier/UBLKCP latency
         // (v1 timeline), more than the MMA time of a 16 KB weight tile. The loads are therefore
-        // spread over lanes: lanes 0..7 own weight-tile loads j = lane, lane+8, ..., lanes 8..11 own
-        // activation panels p = lane-8, lane-4, ... Ring slot and phase follow from the load index,
-        // so the lanes never have to agree on anything.
+        // spread over lanes: lanes 0..b_lanes-1 own weight-tile loads j = lane, lane+b_lanes, ..., lanes
+        // 8..8+a_lanes-1 own activation panels. The lane count divides the ring size, so a ring slot is
+        // always refilled by the SAME lane, in order: a parity wait is only valid one phase ahead, and a
+        // lane two laps ahead of the consumer would sail through it (that was a real bug, session 7).
         const int n_items = first < args.n_work ? (args.n_work - first + stride - 1) / stride : 0;
         const uint8_t* wtiles = reinterpret_cast<const uint8_t*>(args.w) +
                                 static_cast<size_t>(ntile) * n_btiles * btile_bytes;
@@ -103,8 +107,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 for (int i = lane; i < n_btiles; i += 8)
                     bulk_load_1d(smem_b + i * btile_bytes, wtiles + static_cast<size_t>(i) * btile_bytes, btile_bytes, w_full);
             } else {
-                const uint32_t total = static_cast<uint32_t>(n_items) * n_btiles;
-                for (uint32_t j = lane; j < total; j += 8) {
+                const uint32_t total = lane < args.b_lanes ? static_cast<uint32_t>(n_items) * n_btiles : 0u;
+                for (uint32_t j = lane; j < total; j += args.b_lanes) {
                     const int q = static_cast<int>(j % static_cast<uint32_t>(n_btiles));
                     const uint32_t lap = j / static_cast<uint32_t>(args.b_stages);
                     const int sb = static_cast<int>(j - lap * args.b_stages);
@@ -116,8 +120,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             }
         } else if (lane < 12) {
             const int per_item = args.n_chunks * args.rpp;
-            const uint32_t total = static_cast<uint32_t>(n_items) * per_item;
-            for (uint32_t p = lane - 8; p < total; p += 4) {
+            const uint32_t total = lane - 8 < args.a_lanes ? static_cast<uint32_t>(n_items) * per_item : 0u;
+            for (uint32_t p = lane - 8; p < total; p += args.a_lanes) {
                 const int item = static_cast<int>(p / static_cast<uint32_t>(per_item));
                 const int rem = static_cast<int>(p - static_cast<uint32_t>(item) * per_item);
                 const int c = rem / args.rpp, r = rem - c * args.rpp;
@@ -308,16 +312,35 @@ int conv_forward_tc2(const ConvLayer& L, const ConvRuntime& rt, const __half* in
             TTSB_REQUIRE(L.tap_off[c][i] - L.tap_off[c][i - 1] == step[c], "tap offsets must be equally spaced");
     }
 
-    CUtensorMap tm;
-    cuuint64_t dims[3] = {static_cast<cuuint64_t>(L.cin), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(B)};
-    cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld_in) * 2, static_cast<cuuint64_t>(T) * ld_in * 2};
-    cuuint32_t box[3] = {static_cast<cuuint32_t>(L.chunk_k), static_cast<cuuint32_t>(L.rows_panel), 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(in), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     L.chunk_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    TTSB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r)));
+    // tensor maps are pure functions of (pointer, geometry): memoise them, the same workspace buffers
+    // come back every step (host time matters once a step is ~10^3 launches of ~50 us)
+    struct TmKey {
+        const void* p; int ld, B, T, cin, ck, rows;
+        bool operator==(const TmKey& o) const {
+            return p == o.p && ld == o.ld && B == o.B && T == o.T && cin == o.cin && ck == o.ck && rows == o.rows;
+        }
+    };
+    static thread_local std::vector<std::pair<TmKey, CUtensorMap>> cache;
+    const TmKey key{in, ld_in, B, T, L.cin, L.chunk_k, L.rows_panel};
+    const CUtensorMap* tmp = nullptr;
+    for (auto& kv : cache)
+        if (kv.first == key) { tmp = &kv.second; break; }
+    if (tmp == nullptr) {
+        CUtensorMap tm_new;
+        cuuint64_t dims[3] = {static_cast<cuuint64_t>(L.cin), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(B)};
+        cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld_in) * 2, static_cast<cuuint64_t>(T) * ld_in * 2};
+        cuuint32_t box[3] = {static_cast<cuuint32_t>(L.chunk_k), static_cast<cuuint32_t>(L.rows_panel), 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&tm_new, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(in), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         L.chunk_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        TTSB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r)));
+        if (cache.size() >= 256) cache.clear();
+        cache.emplace_back(key, tm_new);
+        tmp = &cache.back().second;
+    }
+    const CUtensorMap& tm = *tmp;
 
     ConvTc2Args a;
     a.B = B; a.T = T;
@@ -332,6 +355,9 @@ int conv_forward_tc2(const ConvLayer& L, const ConvRuntime& rt, const __half* in
     a.n_tile = L.n_tile; a.n_sub = L.n_sub;
     a.a_slots = L.a_slots2; a.b_stages = L.b_stages2;
     a.acc_bufs = L.acc_bufs;
+    a.a_lanes = 1; a.b_lanes = 1;
+    for (int d = 2; d <= 4; ++d) if (a.a_slots % d == 0) a.a_lanes = d;
+    for (int d = 2; d <= 8; ++d) if (a.b_stages % d == 0) a.b_lanes = d;
     a.class_split = L.class_split;
     a.halo_lo = L.halo_lo;
     for (int c = 0; c < 2; ++c) {
