@@ -96,10 +96,12 @@ int conv_layer_create(ConvLayer& L, int cin_logical, int cin_stored, int n_total
         const size_t bar_bytes = 1024 + 1024;
         const size_t w_all = static_cast<size_t>(total_b) * btile;
         const int min_a = std::min(L.n_chunks, 2);
+        const size_t third = kSmemMax / 3 - 2048;
         const bool can2 = min_a * panel + 2 * btile + bar_bytes <= half && n_tile <= 256;
+        const bool can3 = min_a * panel + std::min(3, total_b) * btile + bar_bytes <= third && 2 * n_tile <= 128;
         L.occ2 = can2 ? 2 : 1;
-        if (const char* e = getenv("TTSB_OCC2")) L.occ2 = std::max(1, std::min(atoi(e), can2 ? 2 : 1));
-        const size_t bud = std::min(budget, L.occ2 == 2 ? half : full) - bar_bytes;
+        if (const char* e = getenv("TTSB_OCC2")) L.occ2 = std::max(1, std::min(atoi(e), can3 ? 3 : (can2 ? 2 : 1)));
+        const size_t bud = std::min(budget, L.occ2 == 3 ? third : (L.occ2 == 2 ? half : full)) - bar_bytes;
         int want_res = w_all + std::min(L.n_chunks + 1, 2 * L.n_chunks) * panel <= bud ? 1 : 0;
         if (const char* e = getenv("TTSB_RESIDENT")) want_res = want_res && atoi(e) != 0;
         L.resident = want_res;
@@ -109,7 +111,7 @@ int conv_layer_create(ConvLayer& L, int cin_logical, int cin_stored, int n_total
             if (!L.resident && L.occ2 == 1 && (v == 1 || v == 2 || v == 4) && v * n_tile <= 512) rpp = v;
         }
         L.rpp = rpp;
-        const int tmem_cap = L.occ2 == 2 ? 256 : 512;
+        const int tmem_cap = L.occ2 == 3 ? 128 : (L.occ2 == 2 ? 256 : 512);
         L.acc_bufs = 2 * rpp * n_tile <= tmem_cap ? 2 : 1;
         L.tmem_cols2 = 32;
         while (L.tmem_cols2 < L.acc_bufs * rpp * n_tile) L.tmem_cols2 *= 2;
@@ -121,7 +123,7 @@ int conv_layer_create(ConvLayer& L, int cin_logical, int cin_stored, int n_total
             L.smem_bytes2 = 1024 + as2 * panel + w_all + (2 * as2 + 2 + 5) * 8 + 16;
         } else {
             const int item = rpp * L.n_chunks;                 // panels of one work item
-            const int min_b = std::min(L.occ2 == 2 ? 3 : 4, total_b);
+            const int min_b = std::min(L.occ2 >= 2 ? 3 : 4, total_b);
             int as2 = 2 * item;                                // two work items in flight
             if (as2 * panel + min_b * btile > bud) as2 = item + rpp;      // + the next item's first chunk
             if (as2 * panel + min_b * btile > bud) as2 = item;
@@ -242,7 +244,7 @@ __global__ void __launch_bounds__(128) conv_simt_epilogue_kernel(const EpiParams
     const int t = blockIdx.x * 128 + threadIdx.x;
     const bool ok = t < e.T;
     GmemAcc acc{ok ? scratch + (static_cast<size_t>(b) * e.T + t) * e.n_total + ntile * n_tile : nullptr};
-    run_epilogue(e, acc, b, t, ok, ntile * n_tile, n_tile, [] {});
+    run_epilogue(e, acc, b, t, ok, ntile * n_tile, n_tile, [] {}, [] {});
 }
 
 static int conv_forward_simt(const ConvLayer& L, const ConvRuntime& rt, const __half* in, int ld_in,

@@ -200,7 +200,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             acc.load(0, v);
             if (v[0] == 1234.5678f && args.epi.out_raw) args.epi.out_raw[0] = __float2half(v[1]);
         } else {
-            run_epilogue(args.epi, acc, b, t, t < args.T, ntile * args.n_tile, args.n_tile, wait_acc);
+            run_epilogue(args.epi, acc, b, t, t < args.T, ntile * args.n_tile, args.n_tile, wait_acc, [] {});
         }
     }
     if (threadIdx.x == 64) tl_mark(args, 6);

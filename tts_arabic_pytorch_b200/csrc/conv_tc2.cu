@@ -46,8 +46,8 @@ struct ConvTc2Args {
     EpiParams epi;
 };
 
-template <int kTmemCols>
-__global__ void __launch_bounds__(192, 1)
+template <int kTmemCols, int kMinBlocks>
+__global__ void __launch_bounds__(192, kMinBlocks)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ ConvTc2Args args) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_u32 = smem_u32(smem_raw);
@@ -225,10 +225,24 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         int buf = 0;
         uint32_t pf0 = 0, pf1 = 0;
         const int buf_cols = args.rpp * args.n_tile;
+        const int n_base = ntile * args.n_tile;
+        // cross-tile prefetch (rpp == 1): the next tile's first residual/MRF chunk is requested before
+        // this tile's accumulator is even waited for, so its HBM/L2 latency hides behind a whole tile
+        EpiPrefetch pre_cur, pre_nxt;
+        if (args.rpp == 1 && first < args.n_work) {
+            const int b0 = first / args.groups_t;
+            const int t0 = (first - b0 * args.groups_t) * kTileM + q * 32 + lane;
+            epilogue_prefetch(args.epi, b0, t0, t0 < args.T, n_base, pre_cur);
+        }
         for (int idx = first; idx < args.n_work; idx += stride) {
             const int b = idx / args.groups_t;
             const int tile0 = (idx - b * args.groups_t) * args.rpp;
             const uint32_t par = buf ? pf1 : pf0;
+            if (args.rpp == 1 && idx + stride < args.n_work) {
+                const int bn = (idx + stride) / args.groups_t;
+                const int tn = (idx + stride - bn * args.groups_t) * kTileM + q * 32 + lane;
+                epilogue_prefetch(args.epi, bn, tn, tn < args.T, n_base, pre_nxt);
+            }
             for (int r = 0; r < args.rpp; ++r) {
                 const int t = (tile0 + r) * kTileM + q * 32 + lane;
                 TmemAcc acc{tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * buf_cols + r * args.n_tile};
@@ -238,13 +252,19 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         tc_fence_after();
                     }
                 };
-                run_epilogue(args.epi, acc, b, t, t < args.T, ntile * args.n_tile, args.n_tile, wait_acc);
+                auto drained = [&] {
+                    if (r == args.rpp - 1) {
+                        // every TMEM read of this warp has completed (tcgen05.wait::ld in acc.load)
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                    }
+                };
+                run_epilogue(args.epi, acc, b, t, t < args.T, n_base, args.n_tile, wait_acc, drained,
+                             args.rpp == 1 ? &pre_cur : nullptr);
             }
+            pre_cur = pre_nxt;
             if (buf) pf1 ^= 1; else pf0 ^= 1;
-            // all TMEM reads of this warp are complete (tcgen05.wait::ld inside acc.load)
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
             if (args.acc_bufs == 2) buf ^= 1;
         }
     }
@@ -284,15 +304,15 @@ static int num_sms() {
     return n;
 }
 
-template <int kCols>
+template <int kCols, int kMinBlocks>
 static int launch_two(const CUtensorMap& tm, const ConvTc2Args& a, int grid, size_t smem, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
-        TTSB_CHECK_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<kCols>,
+        TTSB_CHECK_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<kCols, kMinBlocks>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         configured = true;
     }
-    conv_tc2_kernel<kCols><<<grid, 192, smem, s>>>(tm, a);
+    conv_tc2_kernel<kCols, kMinBlocks><<<grid, 192, smem, s>>>(tm, a);
     count_launch();
     TTSB_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -372,12 +392,30 @@ int conv_forward_tc2(const ConvLayer& L, const ConvRuntime& rt, const __half* in
     if (ctas > total) ctas = static_cast<int>(total);
     ctas = (ctas / a.n_tiles_n) * a.n_tiles_n;
     if (ctas < a.n_tiles_n) ctas = a.n_tiles_n;
+    // the register cap follows the planned CTAs per SM (1: 255, 2: 168, 3: 112 registers per thread)
+    if (L.occ2 >= 3) {
+        switch (L.tmem_cols2) {
+            case 32: return launch_two<32, 3>(tm, a, ctas, L.smem_bytes2, stream);
+            case 64: return launch_two<64, 3>(tm, a, ctas, L.smem_bytes2, stream);
+            case 128: return launch_two<128, 3>(tm, a, ctas, L.smem_bytes2, stream);
+        }
+        TTSB_REQUIRE(false, "occupancy 3 needs <= 128 TMEM columns");
+    }
+    if (L.occ2 == 2) {
+        switch (L.tmem_cols2) {
+            case 32: return launch_two<32, 2>(tm, a, ctas, L.smem_bytes2, stream);
+            case 64: return launch_two<64, 2>(tm, a, ctas, L.smem_bytes2, stream);
+            case 128: return launch_two<128, 2>(tm, a, ctas, L.smem_bytes2, stream);
+            case 256: return launch_two<256, 2>(tm, a, ctas, L.smem_bytes2, stream);
+        }
+        TTSB_REQUIRE(false, "occupancy 2 needs <= 256 TMEM columns");
+    }
     switch (L.tmem_cols2) {
-        case 32: return launch_two<32>(tm, a, ctas, L.smem_bytes2, stream);
-        case 64: return launch_two<64>(tm, a, ctas, L.smem_bytes2, stream);
-        case 128: return launch_two<128>(tm, a, ctas, L.smem_bytes2, stream);
-        case 256: return launch_two<256>(tm, a, ctas, L.smem_bytes2, stream);
-        case 512: return launch_two<512>(tm, a, ctas, L.smem_bytes2, stream);
+        case 32: return launch_two<32, 1>(tm, a, ctas, L.smem_bytes2, stream);
+        case 64: return launch_two<64, 1>(tm, a, ctas, L.smem_bytes2, stream);
+        case 128: return launch_two<128, 1>(tm, a, ctas, L.smem_bytes2, stream);
+        case 256: return launch_two<256, 1>(tm, a, ctas, L.smem_bytes2, stream);
+        case 512: return launch_two<512, 1>(tm, a, ctas, L.smem_bytes2, stream);
     }
     TTSB_REQUIRE(false, "bad tmem_cols");
     return 1;

@@ -106,10 +106,25 @@ __device__ __forceinline__ void bias8(const float* bias, int n, float (&f)[8]) {
 // warp-collective, so out-of-range threads still walk the loop but never touch memory).
 // n_base: first logical column of this N tile; n_tile: its width (multiple of 32).
 // `wait_acc()` blocks until the accumulator is complete; it is called AFTER the first chunk of the
-// residual / MRF rows has been requested from HBM.
-template <class Acc, class WaitFn>
+// residual / MRF rows has been requested from HBM. `acc_drained()` is called right after the last
+// read of the accumulator (before the final chunk's math and stores) so a persistent kernel can hand
+// the TMEM buffer back to the MMA warp as early as possible. `pre` (optional) carries a first chunk
+// that the caller already requested (cross-tile prefetch).
+struct EpiPrefetch {
+    Chunk32 res, mrf;
+};
+__device__ __forceinline__ void epilogue_prefetch(const EpiParams& e, int b, int t, bool row_ok, int n_base,
+                                                  EpiPrefetch& out) {
+    const long row = static_cast<long>(b) * e.T + t;
+    const bool use_mrf = e.mrf_mode == MRF_ADD || e.mrf_mode == MRF_LAST;
+    prefetch32(e.residual + row * e.ld_res + n_base, e.residual != nullptr && row_ok, out.res);
+    prefetch32(e.mrf_buf + row * e.n_total + n_base, use_mrf && row_ok, out.mrf);
+}
+
+template <class Acc, class WaitFn, class DrainFn>
 __device__ __forceinline__ void run_epilogue(const EpiParams& e, const Acc& acc, int b, int t,
-                                             bool row_ok, int n_base, int n_tile, WaitFn wait_acc) {
+                                             bool row_ok, int n_base, int n_tile, WaitFn wait_acc,
+                                             DrainFn acc_drained, const EpiPrefetch* pre = nullptr) {
     const long row = static_cast<long>(b) * e.T + t;
     bool in_len = true;
     if (e.lens != nullptr && row_ok) in_len = t < e.lens[b] * e.len_mul;
@@ -120,8 +135,13 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& e, const Acc& acc,
     __half* mrf_row = e.mrf_mode != MRF_NONE ? e.mrf_buf + row * e.n_total + n_base : nullptr;
 
     Chunk32 res_cur, mrf_cur;
-    prefetch32(res_row, use_res, res_cur);
-    prefetch32(mrf_row, use_mrf && row_ok, mrf_cur);
+    if (pre != nullptr) {
+        res_cur = pre->res;
+        mrf_cur = pre->mrf;
+    } else {
+        prefetch32(res_row, use_res, res_cur);
+        prefetch32(mrf_row, use_mrf && row_ok, mrf_cur);
+    }
     wait_acc();
 
     float mean = 0.f, rstd = 1.f;
@@ -168,6 +188,7 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& e, const Acc& acc,
         prefetch32(mrf_row + c0 + 32, use_mrf && row_ok && more, mrf_nxt);
         __syncwarp();
         acc.load(c0, v);
+        if (!more) acc_drained();
         if (row_ok) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
