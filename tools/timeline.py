@@ -43,19 +43,17 @@ def main():
         lib.ttsb_debug_set_timeline(None)
         t = tl.cpu().view(256, 64)
         t0 = int(t[:, 0][t[:, 0] > 0].min())
-        names = {0: 'start', 1: 'setup_done', 2: 'first_B_issued', 3: 'producer_done', 4: 'mma_all_issued',
-                 5: 'epi_sees_acc', 6: 'epi_done', 7: 'cta_end'}
-        print('layer %s: clock64 cycles relative to the earliest CTA start' % name)
-        for cta in [0, 1, 73, 147, 148, 149, 200, 255]:
+        print('layer %s (conv_tc2): cycles relative to each CTA start; per tile: mma[gotTMEM gotA issued] '
+              'epi[wait seen drained done] panel_issued' % name)
+        for cta in [0, 1, 147, 148, 200, 255]:
             row = t[cta]
             if int(row[0]) == 0:
                 continue
             base = int(row[0])
-            s = 'cta %3d  start@%7d | ' % (cta, base - t0)
-            s += ' '.join('%s=%d' % (names[i], int(row[i]) - base) for i in range(1, 8) if int(row[i]) > 0)
-            print(s)
-            mm = [int(row[8 + i]) - base for i in range(41) if int(row[8 + i]) > 0]
-            print('         mma_wait_done[i]:', mm[:24])
+            print('cta %3d start@%d setup=%d' % (cta, base - t0, int(row[1]) - base))
+            for i in range(7):
+                v = [int(row[8 + i * 8 + k]) - base if int(row[8 + i * 8 + k]) > 0 else -1 for k in range(8)]
+                print('    tile %d  mma %6d %6d %6d | epi %6d %6d %6d %6d | panel %6d' % (i, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]))
 
 
 if __name__ == '__main__':

@@ -43,8 +43,16 @@ struct ConvTc2Args {
     int halo_lo;
     const __half* w;
     int* err_flag;
+    long long* timeline;   // debug (tools/timeline.py): 64 clock64() slots per CTA for the first 256 CTAs, or null
     EpiParams epi;
 };
+
+// slot = 8 + tile*8 + k for the CTA's first 7 tiles; k: 0 mma got TMEM, 1 mma got A, 2 mma issued all,
+// 3 epilogue starts waiting, 4 accumulator seen, 5 TMEM handed back, 6 epilogue done, 7 panel load issued
+__device__ __forceinline__ void tl2_mark(const ConvTc2Args& a, int slot) {
+    if (a.timeline == nullptr) return;
+    if (blockIdx.x < 256 && slot < 64) a.timeline[blockIdx.x * 64 + slot] = clock64();
+}
 
 template <int kTmemCols, int kMinBlocks>
 __global__ void __launch_bounds__(192, kMinBlocks)
@@ -76,6 +84,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const int stride = gridDim.x / args.n_tiles_n;
 
     if (warp == 0 && lane == 0) {
+        tl2_mark(args, 0);
         tma_prefetch_desc(&tmap_a);
         for (int i = 0; i < args.a_slots; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
         for (int i = 0; i < args.b_stages; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
@@ -88,6 +97,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) tl2_mark(args, 1);
 
     if (warp == 0) {
         // ---------------- TMA producers ----------------
@@ -134,6 +144,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 mbar_expect_tx(&full_a[sa], panel_bytes);
                 tma_load_3d(smem_a + sa * panel_bytes, &tmap_a, &full_a[sa], c * args.chunk_k,
                             (tile0 + r) * kTileM - args.halo_lo, b);
+                if (c == 0 && r == 0 && item < 7) tl2_mark(args, 8 + item * 8 + 7);
             }
         }
     } else if (warp == 1) {
@@ -160,9 +171,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 mbar_wait(w_full, 0, args.err_flag, 207);
                 tc_fence_after();
             }
-            for (int idx = first; idx < args.n_work; idx += stride) {
+            int tl_i = 0;
+            for (int idx = first; idx < args.n_work; idx += stride, ++tl_i) {
                 mbar_wait(&tmem_empty[buf], buf ? pe1 : pe0, args.err_flag, 203);
                 tc_fence_after();
+                if (tl_i < 7) tl2_mark(args, 8 + tl_i * 8 + 0);
                 if (buf) pe1 ^= 1; else pe0 ^= 1;
                 const uint32_t d_tmem = tmem_base + buf * buf_cols;
                 uint32_t accumulate = 0;
@@ -179,6 +192,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         }
                     }
                     tc_fence_after();
+                    if (c == 0 && tl_i < 7) tl2_mark(args, 8 + tl_i * 8 + 1);
                     for (int tap = 0; tap < args.n_taps; ++tap) {
                         uint32_t b_lo;
                         if (args.resident) {
@@ -216,6 +230,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         if (r < args.rpp) umma_commit(&empty_a[a_slot[r]]);
                 }
                 umma_commit(&tmem_full[buf]);
+                if (tl_i < 7) tl2_mark(args, 8 + tl_i * 8 + 2);
                 if (args.acc_bufs == 2) buf ^= 1;
             }
         }
@@ -226,23 +241,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         uint32_t pf0 = 0, pf1 = 0;
         const int buf_cols = args.rpp * args.n_tile;
         const int n_base = ntile * args.n_tile;
-        // cross-tile prefetch (rpp == 1): the next tile's first residual/MRF chunk is requested before
-        // this tile's accumulator is even waited for, so its HBM/L2 latency hides behind a whole tile
-        EpiPrefetch pre_cur, pre_nxt;
-        if (args.rpp == 1 && first < args.n_work) {
-            const int b0 = first / args.groups_t;
-            const int t0 = (first - b0 * args.groups_t) * kTileM + q * 32 + lane;
-            epilogue_prefetch(args.epi, b0, t0, t0 < args.T, n_base, pre_cur);
-        }
-        for (int idx = first; idx < args.n_work; idx += stride) {
+        int tl_i = 0;
+        const bool tl_on = threadIdx.x == 64;
+        for (int idx = first; idx < args.n_work; idx += stride, ++tl_i) {
             const int b = idx / args.groups_t;
             const int tile0 = (idx - b * args.groups_t) * args.rpp;
             const uint32_t par = buf ? pf1 : pf0;
-            if (args.rpp == 1 && idx + stride < args.n_work) {
-                const int bn = (idx + stride) / args.groups_t;
-                const int tn = (idx + stride - bn * args.groups_t) * kTileM + q * 32 + lane;
-                epilogue_prefetch(args.epi, bn, tn, tn < args.T, n_base, pre_nxt);
-            }
+            if (tl_on && tl_i < 7) tl2_mark(args, 8 + tl_i * 8 + 3);
             for (int r = 0; r < args.rpp; ++r) {
                 const int t = (tile0 + r) * kTileM + q * 32 + lane;
                 TmemAcc acc{tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * buf_cols + r * args.n_tile};
@@ -250,6 +255,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     if (r == 0) {
                         mbar_wait(&tmem_full[buf], par, args.err_flag, 206);
                         tc_fence_after();
+                        if (tl_on && tl_i < 7) tl2_mark(args, 8 + tl_i * 8 + 4);
                     }
                 };
                 auto drained = [&] {
@@ -258,12 +264,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                        if (tl_on && tl_i < 7) tl2_mark(args, 8 + tl_i * 8 + 5);
                     }
                 };
-                run_epilogue(args.epi, acc, b, t, t < args.T, n_base, args.n_tile, wait_acc, drained,
-                             args.rpp == 1 ? &pre_cur : nullptr);
+                // (a cross-tile register prefetch of the next tile's residual was tried in session 9: the
+                // extra 32 live registers pushed the 2-CTA variant into spills and cost 15-20 %)
+                run_epilogue(args.epi, acc, b, t, t < args.T, n_base, args.n_tile, wait_acc, drained);
             }
-            pre_cur = pre_nxt;
+            if (tl_on && tl_i < 7) tl2_mark(args, 8 + tl_i * 8 + 6);
             if (buf) pf1 ^= 1; else pf0 ^= 1;
             if (args.acc_bufs == 2) buf ^= 1;
         }
@@ -385,6 +393,7 @@ int conv_forward_tc2(const ConvLayer& L, const ConvRuntime& rt, const __half* in
         a.step[c] = step[c];
     }
     a.w = L.w_packed; a.err_flag = rt.err_flag; a.epi = epi;
+    a.timeline = rt.timeline;
 
     // persistent grid: `occ` CTAs per SM, a multiple of the number of N tiles
     int ctas = num_sms() * L.occ2;
