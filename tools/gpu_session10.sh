@@ -2,7 +2,7 @@
 set -u
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
-exec > >(tee gpurun_out/session10.log) 2>&1
+exec > >(tee gpurun_out/session11.log) 2>&1
 echo "=== probe"; timeout 900 python tools/probe_conv.py v2
 for L in s3_32_k3_d1 s2_64_k11_d5 s1_128_k11_d5 s0_256_k11_d5; do timeout 120 python tools/timeline.py $L; done
 echo "=== bench_conv default"; timeout 300 python tools/bench_conv.py --only s

@@ -83,7 +83,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const int first = blockIdx.x / args.n_tiles_n;
     const int stride = gridDim.x / args.n_tiles_n;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 0 && elect_one()) {
         tl2_mark(args, 0);
         tma_prefetch_desc(&tmap_a);
         for (int i = 0; i < args.a_slots; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
@@ -100,55 +100,49 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     if (threadIdx.x == 0) tl2_mark(args, 1);
 
     if (warp == 0) {
-        // ---------------- TMA producers ----------------
-        // Issuing one TMA costs the issuing thread ~500 cycles of dependent mbarrier/UBLKCP latency
-        // (v1 timeline), more than the MMA time of a 16 KB weight tile. The loads are therefore
-        // spread over lanes: lanes 0..b_lanes-1 own weight-tile loads j = lane, lane+b_lanes, ..., lanes
-        // 8..8+a_lanes-1 own activation panels. The lane count divides the ring size, so a ring slot is
-        // always refilled by the SAME lane, in order: a parity wait is only valid one phase ahead, and a
-        // lane two laps ahead of the consumer would sail through it (that was a real bug, session 7).
-        const int n_items = first < args.n_work ? (args.n_work - first + stride - 1) / stride : 0;
-        const uint8_t* wtiles = reinterpret_cast<const uint8_t*>(args.w) +
-                                static_cast<size_t>(ntile) * n_btiles * btile_bytes;
-        if (lane < 8) {
+        // ---------------- TMA producer (one elected lane; see the note on elect.sync below) ----------------
+        if (elect_one()) {
+            const uint8_t* wtiles = reinterpret_cast<const uint8_t*>(args.w) +
+                                    static_cast<size_t>(ntile) * n_btiles * btile_bytes;
+            int sa = 0, sb = 0;
+            uint32_t pa = 1, pb = 1;   // parity to wait on the EMPTY barriers (first lap passes)
             if (args.resident) {
-                if (lane == 0) mbar_expect_tx(w_full, n_btiles * btile_bytes);
-                __syncwarp(0xFFu);
-                for (int i = lane; i < n_btiles; i += 8)
+                mbar_expect_tx(w_full, n_btiles * btile_bytes);
+                for (int i = 0; i < n_btiles; ++i)
                     bulk_load_1d(smem_b + i * btile_bytes, wtiles + static_cast<size_t>(i) * btile_bytes, btile_bytes, w_full);
-            } else {
-                const uint32_t total = lane < args.b_lanes ? static_cast<uint32_t>(n_items) * n_btiles : 0u;
-                for (uint32_t j = lane; j < total; j += args.b_lanes) {
-                    const int q = static_cast<int>(j % static_cast<uint32_t>(n_btiles));
-                    const uint32_t lap = j / static_cast<uint32_t>(args.b_stages);
-                    const int sb = static_cast<int>(j - lap * args.b_stages);
-                    mbar_wait(&empty_b[sb], (lap & 1u) ^ 1u, args.err_flag, 202);
-                    mbar_expect_tx(&full_b[sb], btile_bytes);
-                    bulk_load_1d(smem_b + sb * btile_bytes, wtiles + static_cast<size_t>(q) * btile_bytes, btile_bytes,
-                                 &full_b[sb]);
-                }
             }
-        } else if (lane < 12) {
-            const int per_item = args.n_chunks * args.rpp;
-            const uint32_t total = lane - 8 < args.a_lanes ? static_cast<uint32_t>(n_items) * per_item : 0u;
-            for (uint32_t p = lane - 8; p < total; p += args.a_lanes) {
-                const int item = static_cast<int>(p / static_cast<uint32_t>(per_item));
-                const int rem = static_cast<int>(p - static_cast<uint32_t>(item) * per_item);
-                const int c = rem / args.rpp, r = rem - c * args.rpp;
-                const int idx = first + item * stride;
+            int item = 0;
+            for (int idx = first; idx < args.n_work; idx += stride, ++item) {
                 const int b = idx / args.groups_t;
                 const int tile0 = (idx - b * args.groups_t) * args.rpp;
-                const uint32_t lap = p / static_cast<uint32_t>(args.a_slots);
-                const int sa = static_cast<int>(p - lap * args.a_slots);
-                mbar_wait(&empty_a[sa], (lap & 1u) ^ 1u, args.err_flag, 201);
-                mbar_expect_tx(&full_a[sa], panel_bytes);
-                tma_load_3d(smem_a + sa * panel_bytes, &tmap_a, &full_a[sa], c * args.chunk_k,
-                            (tile0 + r) * kTileM - args.halo_lo, b);
-                if (c == 0 && r == 0 && item < 7) tl2_mark(args, 8 + item * 8 + 7);
+                const uint8_t* wp = wtiles;
+                for (int c = 0; c < args.n_chunks; ++c) {
+                    for (int r = 0; r < args.rpp; ++r) {
+                        mbar_wait(&empty_a[sa], pa, args.err_flag, 201);
+                        mbar_expect_tx(&full_a[sa], panel_bytes);
+                        tma_load_3d(smem_a + sa * panel_bytes, &tmap_a, &full_a[sa], c * args.chunk_k,
+                                    (tile0 + r) * kTileM - args.halo_lo, b);
+                        if (c == 0 && r == 0 && item < 7) tl2_mark(args, 8 + item * 8 + 7);
+                        if (++sa == args.a_slots) { sa = 0; pa ^= 1; }
+                    }
+                    if (!args.resident) {
+                        for (int tap = 0; tap < args.n_taps; ++tap) {
+                            mbar_wait(&empty_b[sb], pb, args.err_flag, 202);
+                            mbar_expect_tx(&full_b[sb], btile_bytes);
+                            bulk_load_1d(smem_b + sb * btile_bytes, wp, btile_bytes, &full_b[sb]);
+                            wp += btile_bytes;
+                            if (++sb == args.b_stages) { sb = 0; pb ^= 1; }
+                        }
+                    }
+                }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        // elect.sync (not `lane == 0`): ptxas then knows exactly one lane is active and feeds the
+        // UTCHMMA uniform-register operands with plain R2UR moves; with a threadIdx-derived predicate it
+        // wraps EVERY tcgen05.mma in an ELECT/R2UR.BROADCAST/VOTEU waterfall loop (~260 cycles each,
+        // profiles/r01_s10_timeline_v2.txt)
+        if (elect_one()) {
             // ---------------- MMA issuer ----------------
             const int nsub_cols = args.n_tile / args.n_sub;
             const uint32_t idesc = umma_idesc_f16(kTileM, nsub_cols);
@@ -263,7 +257,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         // every TMEM read of this warp has completed (tcgen05.wait::ld in acc.load)
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                        if (elect_one()) mbar_arrive(&tmem_empty[buf]);
                         if (tl_on && tl_i < 7) tl2_mark(args, 8 + tl_i * 8 + 5);
                     }
                 };
