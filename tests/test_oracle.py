@@ -107,3 +107,20 @@ def test_fastpitch_is_not_batch_invariant(fastpitch_weights_const4):
     a, s, ww = t_b['enc_out'][1, :9], t_s['enc_out'][0], t_w['enc_out'][1, :9]
     assert (a - s).abs().max() > 1e-2          # batch-variant
     assert (a - ww).abs().max() < 1e-4         # but independent of HOW MUCH padding
+
+
+def test_tacotron2_oracle_matches_reference_with_injected_masks(golden_dir):
+    """BASELINE config 4 path (Tacotron2MS.infer + torchaudio decoder), prenet dropout masks injected on
+    both sides, gate held shut so all utterances run the full 24 steps."""
+    from oracle import tacotron2_oracle as t2o
+    g = _load(golden_dir, 'tacotron2_small.npz')
+    sd = synth.tacotron2_state_dict(1236)
+    masks = torch.from_numpy(g['masks']).float() * 2.0
+    mel, mel_lens, align = t2o.tacotron2_infer(sd, torch.from_numpy(g['tokens']), torch.from_numpy(g['speaker_ids']),
+                                               torch.from_numpy(g['lengths']), prenet_masks=masks, max_steps=24)
+    assert mel_lens.tolist() == g['mel_lengths'].tolist() == [24, 24, 24]
+    assert mel.shape == g['mel'].shape == (3, 80, 24)
+    assert np.abs(mel.numpy() - g['mel']).max() < TOL
+    assert np.abs(align.numpy() - g['alignments']).max() < TOL
+    # attention never looks at padded tokens
+    assert float(align[1, :, 10:].abs().max()) == 0.0 and float(align[2, :, 5:].abs().max()) == 0.0

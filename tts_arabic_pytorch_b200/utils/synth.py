@@ -193,6 +193,59 @@ def fastpitch_state_dict(seed=1234, cfg=None, dur_mode='const4'):
     return sd
 
 
+def tacotron2_state_dict(seed=1236, n_symbol=40, num_speakers=40, gate_bias=-3.0):
+    """Tacotron2MS weights with every key of the reference module (tacotron2_ms.py:119-207 +
+    torchaudio _Encoder/_Decoder/_Postnet). `gate_bias` keeps the stop gate shut for synthetic tests
+    (decoding runs a fixed number of steps)."""
+    r = _Rng(seed)
+    sd = OrderedDict()
+    E, H, S, P, Amem, Ahid, NF, KL, M = 512, 1024, 128, 256, 640, 128, 32, 31, 80
+
+    def bn(p, n):
+        sd[p + '.weight'] = 1.0 + r.normal((n,), 0.1)
+        sd[p + '.bias'] = r.normal((n,), 0.1)
+        sd[p + '.running_mean'] = r.normal((n,), 0.1)
+        sd[p + '.running_var'] = 1.0 + r.normal((n,), 0.1).abs()
+        sd[p + '.num_batches_tracked'] = torch.tensor(100)
+
+    sd['embedding.weight'] = r.normal((n_symbol, E), 0.5)
+    for i in range(3):
+        sd['encoder.convolutions.%d.0.weight' % i] = r.normal((E, E, 5), 1.2 / math.sqrt(E * 5))
+        sd['encoder.convolutions.%d.0.bias' % i] = r.normal((E,), 0.05)
+        bn('encoder.convolutions.%d.1' % i, E)
+    for suf in ('', '_reverse'):
+        sd['encoder.lstm.weight_ih_l0' + suf] = r.normal((4 * E // 2, E), 1.0 / math.sqrt(E))
+        sd['encoder.lstm.weight_hh_l0' + suf] = r.normal((4 * E // 2, E // 2), 1.0 / math.sqrt(E // 2))
+        sd['encoder.lstm.bias_ih_l0' + suf] = r.normal((4 * E // 2,), 0.05)
+        sd['encoder.lstm.bias_hh_l0' + suf] = r.normal((4 * E // 2,), 0.05)
+    sd['decoder.prenet.layers.0.weight'] = r.normal((P, M), 1.0 / math.sqrt(M))
+    sd['decoder.prenet.layers.1.weight'] = r.normal((P, P), 1.0 / math.sqrt(P))
+    for name, n_in in (('decoder.attention_rnn', P + Amem), ('decoder.decoder_rnn', H + Amem)):
+        sd[name + '.weight_ih'] = r.normal((4 * H, n_in), 1.0 / math.sqrt(n_in))
+        sd[name + '.weight_hh'] = r.normal((4 * H, H), 1.0 / math.sqrt(H))
+        sd[name + '.bias_ih'] = r.normal((4 * H,), 0.05)
+        sd[name + '.bias_hh'] = r.normal((4 * H,), 0.05)
+        if name == 'decoder.attention_rnn':
+            A = 'decoder.attention_layer.'
+            sd[A + 'query_layer.weight'] = r.normal((Ahid, H), 1.0 / math.sqrt(H))
+            sd[A + 'memory_layer.weight'] = r.normal((Ahid, Amem), 1.0 / math.sqrt(Amem))
+            sd[A + 'v.weight'] = r.normal((1, Ahid), 3.0 / math.sqrt(Ahid))
+            sd[A + 'location_layer.location_conv.weight'] = r.normal((NF, 2, KL), 1.0 / math.sqrt(2 * KL))
+            sd[A + 'location_layer.location_dense.weight'] = r.normal((Ahid, NF), 1.0 / math.sqrt(NF))
+    sd['decoder.linear_projection.weight'] = r.normal((M, H + Amem), 1.0 / math.sqrt(H + Amem))
+    sd['decoder.linear_projection.bias'] = r.normal((M,), 0.1)
+    sd['decoder.gate_layer.weight'] = r.normal((1, H + Amem), 0.2 / math.sqrt(H + Amem))
+    sd['decoder.gate_layer.bias'] = torch.full((1,), float(gate_bias))
+    dims = [M, 512, 512, 512, 512, M]
+    for i in range(5):
+        sd['postnet.convolutions.%d.0.weight' % i] = r.normal((dims[i + 1], dims[i], 5), 1.0 / math.sqrt(dims[i] * 5))
+        sd['postnet.convolutions.%d.0.bias' % i] = r.normal((dims[i + 1],), 0.05)
+        bn('postnet.convolutions.%d.1' % i, dims[i + 1])
+    if num_speakers > 1:
+        sd['speaker_embedding.weight'] = r.normal((num_speakers, S), 0.3)
+    return sd
+
+
 def write_checkpoints(directory, seed=1234, dur_mode='const4'):
     """Writes fastpitch.pth + hifigan.pth (+ config.json) in the reference's formats; returns paths."""
     import json
