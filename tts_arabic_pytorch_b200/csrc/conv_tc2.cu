@@ -76,6 +76,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     uint64_t* tmem_empty = tmem_full + 2;            // [2]
     uint64_t* w_full = tmem_empty + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+    // 4 x 2 KB staging tiles for the epilogue warps' coalesced row I/O (epilogue.cuh)
+    uint8_t* smem_stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 127) & ~static_cast<uintptr_t>(127));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -263,7 +265,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 };
                 // (a cross-tile register prefetch of the next tile's residual was tried in session 9: the
                 // extra 32 live registers pushed the 2-CTA variant into spills and cost 15-20 %)
-                run_epilogue(args.epi, acc, b, t, t < args.T, n_base, args.n_tile, wait_acc, drained);
+                run_epilogue(args.epi, acc, b, t, t < args.T, n_base, args.n_tile, wait_acc, drained,
+                             smem_stage + q * 2048);
             }
             if (tl_on && tl_i < 7) tl2_mark(args, 8 + tl_i * 8 + 6);
             if (buf) pf1 ^= 1; else pf0 ^= 1;

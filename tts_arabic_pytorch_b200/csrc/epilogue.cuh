@@ -77,19 +77,81 @@ __device__ __forceinline__ void store8h(__half* p, const float* f) {
     *reinterpret_cast<uint4*>(p) = u;
 }
 
-// Raw 16-byte prefetch of one 32-column chunk of a fp16 row (4 x uint4), issued early so that the
-// global-load latency overlaps the MMA phase / the previous chunk's math.
+// ------------------------------------------------------------------------------------------------
+// Row I/O of one warp: 32 rows x 32 fp16 columns (64 B per row) per step.
+//
+// In the accumulator layout lane == row, so a naive 16-byte global access per lane touches 32
+// different 128-byte lines per instruction; the v2 timelines (profiles/r01_s11_timeline_v2_elect.txt)
+// show the epilogue bound by exactly that line-request rate (5.7k cycles to retire the stores of a
+// 128x32 tile). With a per-warp 2 KB staging tile the global side is issued "transposed": lane l of
+// step i moves 16-byte unit (i*32 + l) of the row-major block -> 8 rows x 64 B per instruction
+// (4 full lines when rows are contiguous, C = 32; 8 half lines otherwise) instead of 32 lines.
+// The tile is XOR-swizzled so both the row-owner and the transposed accesses are conflict-free.
+// ------------------------------------------------------------------------------------------------
 struct Chunk32 {
     uint4 q[4];
 };
-__device__ __forceinline__ void prefetch32(const __half* p, bool on, Chunk32& c) {
+__device__ __forceinline__ uint32_t wtile_off(int r, int u) { return r * 64 + ((u ^ ((r >> 1) & 3)) << 4); }
+
+struct RowIO {
+    uint8_t* tile;      // this warp's 2 KB staging tile, or null -> direct per-row access
+    int lane;
+    int rows_valid;     // rows of this warp inside [0, T): clamp(T - warp_row0, 0, 32)
+
+    // request a [32 x 32] block whose (row 0, col 0) element is at `blk` (row pitch ld elements)
+    __device__ __forceinline__ void request(const __half* blk, long ld, bool on, Chunk32& c) const {
 #pragma unroll
-    for (int g = 0; g < 4; ++g)
-        c.q[g] = on ? *(reinterpret_cast<const uint4*>(p) + g) : make_uint4(0, 0, 0, 0);
-}
+        for (int i = 0; i < 4; ++i) {
+            int r, u;
+            if (tile) { const int id = i * 32 + lane; r = id >> 2; u = id & 3; } else { r = lane; u = i; }
+            c.q[i] = (on && r < rows_valid) ? *reinterpret_cast<const uint4*>(blk + r * ld + u * 8) : make_uint4(0, 0, 0, 0);
+        }
+    }
+    // turn a requested block into this lane's own row (4 units of 8 columns)
+    __device__ __forceinline__ void to_row(Chunk32& c) const {
+        if (!tile) return;
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int id = i * 32 + lane;
+            *reinterpret_cast<uint4*>(tile + wtile_off(id >> 2, id & 3)) = c.q[i];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) c.q[u] = *reinterpret_cast<const uint4*>(tile + wtile_off(lane, u));
+    }
+    // write this lane's own row (4 units) of a [32 x 32] block
+    __device__ __forceinline__ void store(__half* blk, long ld, const Chunk32& own) const {
+        if (!tile) {
+            if (lane < rows_valid) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(blk + lane * ld + u * 8) = own.q[u];
+            }
+            return;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(tile + wtile_off(lane, u)) = own.q[u];
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int id = i * 32 + lane;
+            const int r = id >> 2, u = id & 3;
+            const uint4 v = *reinterpret_cast<const uint4*>(tile + wtile_off(r, u));
+            if (r < rows_valid) *reinterpret_cast<uint4*>(blk + r * ld + u * 8) = v;
+        }
+    }
+};
+
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
     float2 a = unpack_half2(u.x), b = unpack_half2(u.y), c = unpack_half2(u.z), d = unpack_half2(u.w);
     f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+    uint4 u;
+    u.x = pack_half2(f[0], f[1]); u.y = pack_half2(f[2], f[3]);
+    u.z = pack_half2(f[4], f[5]); u.w = pack_half2(f[6], f[7]);
+    return u;
 }
 __device__ __forceinline__ void bias8(const float* bias, int n, float (&f)[8]) {
     if (bias == nullptr) {
@@ -102,46 +164,33 @@ __device__ __forceinline__ void bias8(const float* bias, int n, float (&f)[8]) {
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
 
-// b: utterance, t: row inside the utterance, row_ok: t < T (loads from the accumulator are
-// warp-collective, so out-of-range threads still walk the loop but never touch memory).
-// n_base: first logical column of this N tile; n_tile: its width (multiple of 32).
-// `wait_acc()` blocks until the accumulator is complete; it is called AFTER the first chunk of the
-// residual / MRF rows has been requested from HBM. `acc_drained()` is called right after the last
-// read of the accumulator (before the final chunk's math and stores) so a persistent kernel can hand
-// the TMEM buffer back to the MMA warp as early as possible. `pre` (optional) carries a first chunk
-// that the caller already requested (cross-tile prefetch).
-struct EpiPrefetch {
-    Chunk32 res, mrf;
-};
-__device__ __forceinline__ void epilogue_prefetch(const EpiParams& e, int b, int t, bool row_ok, int n_base,
-                                                  EpiPrefetch& out) {
-    const long row = static_cast<long>(b) * e.T + t;
-    const bool use_mrf = e.mrf_mode == MRF_ADD || e.mrf_mode == MRF_LAST;
-    prefetch32(e.residual + row * e.ld_res + n_base, e.residual != nullptr && row_ok, out.res);
-    prefetch32(e.mrf_buf + row * e.n_total + n_base, use_mrf && row_ok, out.mrf);
-}
-
+// b: utterance, t: row inside the utterance (lane i of the warp owns row t = warp_row0 + i), row_ok:
+// t < T (loads from the accumulator are warp-collective, so out-of-range threads still walk the loop
+// but never touch memory). n_base: first logical column of this N tile; n_tile: its width (multiple
+// of 32). `wait_acc()` blocks until the accumulator is complete; it is called AFTER the first chunk
+// of the residual / MRF rows has been requested from HBM. `acc_drained()` is called right after the
+// last read of the accumulator so a persistent kernel can hand the TMEM buffer back early.
+// `stage`: this warp's 2 KB staging tile for coalesced row I/O (null = direct access).
 template <class Acc, class WaitFn, class DrainFn>
 __device__ __forceinline__ void run_epilogue(const EpiParams& e, const Acc& acc, int b, int t,
                                              bool row_ok, int n_base, int n_tile, WaitFn wait_acc,
-                                             DrainFn acc_drained, const EpiPrefetch* pre = nullptr) {
-    const long row = static_cast<long>(b) * e.T + t;
+                                             DrainFn acc_drained, uint8_t* stage = nullptr) {
+    const int lane = threadIdx.x & 31;
+    const int warp_row0 = t - lane;
+    const long row0 = static_cast<long>(b) * e.T + warp_row0;      // first row of this warp
+    const long row = row0 + lane;
     bool in_len = true;
     if (e.lens != nullptr && row_ok) in_len = t < e.lens[b] * e.len_mul;
     const bool do_ln = e.ln_g != nullptr;
-    const __half* res_row = e.residual ? e.residual + row * e.ld_res + n_base : nullptr;
-    const bool use_res = res_row != nullptr && row_ok;
+    RowIO io{stage, lane, min(32, max(0, e.T - warp_row0))};
+    const bool use_res = e.residual != nullptr;
     const bool use_mrf = e.mrf_mode == MRF_ADD || e.mrf_mode == MRF_LAST;
-    __half* mrf_row = e.mrf_mode != MRF_NONE ? e.mrf_buf + row * e.n_total + n_base : nullptr;
+    const __half* res_blk = e.residual + row0 * e.ld_res + n_base;
+    __half* mrf_blk = e.mrf_buf + row0 * e.n_total + n_base;
 
     Chunk32 res_cur, mrf_cur;
-    if (pre != nullptr) {
-        res_cur = pre->res;
-        mrf_cur = pre->mrf;
-    } else {
-        prefetch32(res_row, use_res, res_cur);
-        prefetch32(mrf_row, use_mrf && row_ok, mrf_cur);
-    }
+    io.request(res_blk, e.ld_res, use_res, res_cur);
+    io.request(mrf_blk, e.n_total, use_mrf, mrf_cur);
     wait_acc();
 
     float mean = 0.f, rstd = 1.f;
@@ -151,7 +200,8 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& e, const Acc& acc,
         for (int c0 = 0; c0 < n_tile; c0 += 32) {
             float v[32];
             Chunk32 res_nxt;
-            prefetch32(res_row + c0 + 32, use_res && c0 + 32 < n_tile, res_nxt);
+            io.request(res_blk + c0 + 32, e.ld_res, use_res && c0 + 32 < n_tile, res_nxt);
+            if (use_res) io.to_row(res_cur);
             __syncwarp();
             acc.load(c0, v);
             if (row_ok) {
@@ -184,69 +234,71 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& e, const Acc& acc,
         float v[32];
         Chunk32 res_nxt, mrf_nxt;
         const bool more = c0 + 32 < n_tile;
-        prefetch32(res_row + c0 + 32, use_res && !do_ln && more, res_nxt);
-        prefetch32(mrf_row + c0 + 32, use_mrf && row_ok && more, mrf_nxt);
+        io.request(res_blk + c0 + 32, e.ld_res, use_res && !do_ln && more, res_nxt);
+        io.request(mrf_blk + c0 + 32, e.n_total, use_mrf && more, mrf_nxt);
+        if (use_res && !do_ln) io.to_row(res_cur);
+        if (use_mrf) io.to_row(mrf_cur);
         __syncwarp();
         acc.load(c0, v);
         if (!more) acc_drained();
-        if (row_ok) {
+        Chunk32 o_raw, o_act, o_mrf;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const int n = n_base + c0 + g * 8;
-                float x[8];
-                if (do_ln) {
-                    float gm[8], bt[8];
-                    bias8(e.ln_g, n, gm);
-                    bias8(e.ln_b, n, bt);
+        for (int g = 0; g < 4; ++g) {
+            const int n = n_base + c0 + g * 8;
+            float x[8];
+            if (do_ln) {
+                float gm[8], bt[8];
+                bias8(e.ln_g, n, gm);
+                bias8(e.ln_b, n, bt);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) x[j] = (v[g * 8 + j] - mean) * rstd * gm[j] + bt[j];
-                    if (e.head_w) {
-                        float hw[8];
-                        bias8(e.head_w, n, hw);
+                for (int j = 0; j < 8; ++j) x[j] = (v[g * 8 + j] - mean) * rstd * gm[j] + bt[j];
+                if (e.head_w) {
+                    float hw[8];
+                    bias8(e.head_w, n, hw);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) head += x[j] * hw[j];
-                    }
-                } else {
-                    float r[8], bs[8];
-                    unpack8(res_cur.q[g], r);
-                    bias8(e.bias, n, bs);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) x[j] = v[g * 8 + j] + bs[j] + r[j];
+                    for (int j = 0; j < 8; ++j) head += x[j] * hw[j];
                 }
-                if (e.out_f32_t && e.f32_unmasked) {
+            } else {
+                float r[8], bs[8];
+                unpack8(res_cur.q[g], r);
+                bias8(e.bias, n, bs);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (n + j < e.n_store)
-                            e.out_f32_t[(static_cast<long>(b) * e.n_store + n + j) * e.T + t] = x[j];
-                }
-                if (!in_len) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) x[j] = 0.f;
-                }
-                if (e.mrf_mode != MRF_NONE) {
-                    float m[8];
-                    unpack8(mrf_cur.q[g], m);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) x[j] = m[j] + x[j] * e.mrf_scale;
-                    if (e.mrf_mode != MRF_LAST) {
-                        store8h(mrf_row + c0 + g * 8, x);
-                        continue;
-                    }
-                }
-                if (e.out_raw) store8h(e.out_raw + row * e.ld_raw + n, x);
-                if (e.out_f32_t && !e.f32_unmasked) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (n + j < e.n_store)
-                            e.out_f32_t[(static_cast<long>(b) * e.n_store + n + j) * e.T + t] = x[j];
-                }
-                if (e.out_act) {
-                    float a[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) a[j] = lrelu(x[j], e.act_slope);
-                    store8h(e.out_act + row * e.ld_act + n, a);
-                }
+                for (int j = 0; j < 8; ++j) x[j] = v[g * 8 + j] + bs[j] + r[j];
             }
+            if (e.out_f32_t && e.f32_unmasked && row_ok) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (n + j < e.n_store)
+                        e.out_f32_t[(static_cast<long>(b) * e.n_store + n + j) * e.T + t] = x[j];
+            }
+            if (!in_len) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = 0.f;
+            }
+            if (e.mrf_mode != MRF_NONE) {
+                float m[8];
+                unpack8(mrf_cur.q[g], m);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = m[j] + x[j] * e.mrf_scale;
+                o_mrf.q[g] = pack8(x);
+            }
+            o_raw.q[g] = pack8(x);
+            if (e.out_f32_t && !e.f32_unmasked && row_ok) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (n + j < e.n_store)
+                        e.out_f32_t[(static_cast<long>(b) * e.n_store + n + j) * e.T + t] = x[j];
+            }
+            float a[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = lrelu(x[j], e.act_slope);
+            o_act.q[g] = pack8(a);
+        }
+        if (e.mrf_mode != MRF_NONE && e.mrf_mode != MRF_LAST) {
+            io.store(mrf_blk + c0, e.n_total, o_mrf);
+        } else {
+            if (e.out_raw) io.store(e.out_raw + row0 * e.ld_raw + n_base + c0, e.ld_raw, o_raw);
+            if (e.out_act) io.store(e.out_act + row0 * e.ld_act + n_base + c0, e.ld_act, o_act);
         }
         res_cur = res_nxt;
         mrf_cur = mrf_nxt;
