@@ -36,12 +36,12 @@ def main():
         for _ in range(3):
             _lib.check(lib.ttsb_conv1d_forward(h, _lib.ptr(x), B, T, _lib.ptr(res), 0.1, None, _lib.ptr(out), None))
         torch.cuda.synchronize()
-        tl = torch.zeros(256 * 64, dtype=torch.int64, device=dev)
+        tl = torch.zeros(256 * 128, dtype=torch.int64, device=dev)
         lib.ttsb_debug_set_timeline(_lib.ptr(tl))
         _lib.check(lib.ttsb_conv1d_forward(h, _lib.ptr(x), B, T, _lib.ptr(res), 0.1, None, _lib.ptr(out), None))
         torch.cuda.synchronize()
         lib.ttsb_debug_set_timeline(None)
-        t = tl.cpu().view(256, 64)
+        t = tl.cpu().view(256, 128)
         t0 = int(t[:, 0][t[:, 0] > 0].min())
         print('layer %s (conv_tc2): cycles relative to each CTA start; per tile: mma[gotTMEM gotA issued] '
               'epi[wait seen drained done] panel_issued' % name)
@@ -54,6 +54,8 @@ def main():
             for i in range(7):
                 v = [int(row[8 + i * 8 + k]) - base if int(row[8 + i * 8 + k]) > 0 else -1 for k in range(8)]
                 print('    tile %d  mma %6d %6d %6d | epi %6d %6d %6d %6d | panel %6d' % (i, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]))
+                d = [int(row[64 + i * 8 + k]) - base if int(row[64 + i * 8 + k]) > 0 else -1 for k in range(7)]
+                print('            epi detail: seen %d res_row %d acc_loaded %d drained %d math %d raw_stored %d act_stored %d' % tuple(d))
 
 
 if __name__ == '__main__':

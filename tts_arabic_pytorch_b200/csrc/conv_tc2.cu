@@ -51,7 +51,7 @@ struct ConvTc2Args {
 // 3 epilogue starts waiting, 4 accumulator seen, 5 TMEM handed back, 6 epilogue done, 7 panel load issued
 __device__ __forceinline__ void tl2_mark(const ConvTc2Args& a, int slot) {
     if (a.timeline == nullptr) return;
-    if (blockIdx.x < 256 && slot < 64) a.timeline[blockIdx.x * 64 + slot] = clock64();
+    if (blockIdx.x < 256 && slot < 64) a.timeline[blockIdx.x * 128 + slot] = clock64();
 }
 
 template <int kTmemCols, int kMinBlocks>
@@ -265,8 +265,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 };
                 // (a cross-tile register prefetch of the next tile's residual was tried in session 9: the
                 // extra 32 live registers pushed the 2-CTA variant into spills and cost 15-20 %)
+                long long* dbg = (tl_on && args.timeline != nullptr && blockIdx.x < 256 && tl_i < 7)
+                                     ? args.timeline + blockIdx.x * 128 + 64 + tl_i * 8 : nullptr;
                 run_epilogue(args.epi, acc, b, t, t < args.T, n_base, args.n_tile, wait_acc, drained,
-                             smem_stage + q * 2048);
+                             smem_stage + q * 2048, dbg);
             }
             if (tl_on && tl_i < 7) tl2_mark(args, 8 + tl_i * 8 + 6);
             if (buf) pf1 ^= 1; else pf0 ^= 1;

@@ -41,6 +41,9 @@ struct EpiParams {
     __half* out_act = nullptr;      // lrelu(v, act_slope); slope 0 == relu
     int ld_act = 0;
     float act_slope = 0.f;
+    int act_tanh = 0;               // out_act = tanh(v) instead of leaky-relu (Tacotron2 postnet)
+    float* out_f32 = nullptr;       // v as fp32, row-major [B*T, ld_f32] (LSTM gate pre-activations)
+    int ld_f32 = 0;
     float* out_f32_t = nullptr;     // [B, n_store, T] fp32, transposed store
     int n_store = 0;
     int f32_unmasked = 0;           // out_f32_t receives the value before row masking
@@ -174,7 +177,8 @@ __device__ __forceinline__ void bias8(const float* bias, int n, float (&f)[8]) {
 template <class Acc, class WaitFn, class DrainFn>
 __device__ __forceinline__ void run_epilogue(const EpiParams& e, const Acc& acc, int b, int t,
                                              bool row_ok, int n_base, int n_tile, WaitFn wait_acc,
-                                             DrainFn acc_drained, uint8_t* stage = nullptr) {
+                                             DrainFn acc_drained, uint8_t* stage = nullptr,
+                                             long long* dbg = nullptr) {
     const int lane = threadIdx.x & 31;
     const int warp_row0 = t - lane;
     const long row0 = static_cast<long>(b) * e.T + warp_row0;      // first row of this warp
@@ -192,6 +196,7 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& e, const Acc& acc,
     io.request(res_blk, e.ld_res, use_res, res_cur);
     io.request(mrf_blk, e.n_total, use_mrf, mrf_cur);
     wait_acc();
+    if (dbg) dbg[0] = clock64();
 
     float mean = 0.f, rstd = 1.f;
     if (do_ln) {
@@ -238,9 +243,12 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& e, const Acc& acc,
         io.request(mrf_blk + c0 + 32, e.n_total, use_mrf && more, mrf_nxt);
         if (use_res && !do_ln) io.to_row(res_cur);
         if (use_mrf) io.to_row(mrf_cur);
+        if (dbg && c0 == 0) dbg[1] = clock64();
         __syncwarp();
         acc.load(c0, v);
+        if (dbg && c0 == 0) dbg[2] = clock64();
         if (!more) acc_drained();
+        if (dbg && c0 == 0) dbg[3] = clock64();
         Chunk32 o_raw, o_act, o_mrf;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -289,17 +297,25 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& e, const Acc& acc,
                     if (n + j < e.n_store)
                         e.out_f32_t[(static_cast<long>(b) * e.n_store + n + j) * e.T + t] = x[j];
             }
+            if (e.out_f32 && row_ok) {
+                float4* o = reinterpret_cast<float4*>(e.out_f32 + row * e.ld_f32 + n);
+                o[0] = make_float4(x[0], x[1], x[2], x[3]);
+                o[1] = make_float4(x[4], x[5], x[6], x[7]);
+            }
             float a[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) a[j] = lrelu(x[j], e.act_slope);
+            for (int j = 0; j < 8; ++j) a[j] = e.act_tanh ? tanhf(x[j]) : lrelu(x[j], e.act_slope);
             o_act.q[g] = pack8(a);
         }
+        if (dbg && c0 == 0) dbg[4] = clock64();
         if (e.mrf_mode != MRF_NONE && e.mrf_mode != MRF_LAST) {
             io.store(mrf_blk + c0, e.n_total, o_mrf);
         } else {
             if (e.out_raw) io.store(e.out_raw + row0 * e.ld_raw + n_base + c0, e.ld_raw, o_raw);
+            if (dbg && c0 == 0) dbg[5] = clock64();
             if (e.out_act) io.store(e.out_act + row0 * e.ld_act + n_base + c0, e.ld_act, o_act);
         }
+        if (dbg && c0 == 0) dbg[6] = clock64();
         res_cur = res_nxt;
         mrf_cur = mrf_nxt;
     }
