@@ -31,6 +31,7 @@ extern "C" {
 typedef struct ttsb_hifigan ttsb_hifigan_t;
 typedef struct ttsb_fastpitch ttsb_fastpitch_t;
 typedef struct ttsb_conv1d ttsb_conv1d_t;
+typedef struct ttsb_tacotron2 ttsb_tacotron2_t;
 
 /* A named host fp32 tensor in the reference's own state_dict layout (after weight-norm has been
  * folded, i.e. what remove_weight_norm() leaves: vocoder/__init__.py:19). */
@@ -141,6 +142,30 @@ int ttsb_fastpitch_condition(ttsb_fastpitch_t* h, int B, int L, const float* d_l
  * channel-last copy for ttsb_hifigan_forward (zero beyond each utterance), may be NULL. */
 int ttsb_fastpitch_decode(ttsb_fastpitch_t* h, int B, int L, int T, float* d_mel, void* d_mel_cl,
                           void* d_state, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Tacotron2 (multi-speaker), replaces models.tacotron2.tacotron2_ms.Tacotron2MS.infer
+ * (models/tacotron2/tacotron2_ms.py:278-332; arithmetic of torchaudio 2.11 _Encoder/_Decoder/_Postnet).
+ * Weights: the module's state_dict (BatchNorm running stats included; folded at create()).
+ *   encode   tokens -> encoder memory, decoder state reset
+ *   decode   n autoregressive steps; the prenet's always-on dropout (torchaudio:283-285) takes its
+ *            keep-masks from the caller (d_masks [n_steps, 2, B, 256] bytes, 1 = keep)
+ *   finish   postnet + residual, lengths, alignments
+ * The caller polls `h_done_step` every few steps instead of the reference's per-step host sync.
+ * --------------------------------------------------------------------------------------------- */
+int ttsb_tacotron2_create(const ttsb_tensor_t* weights, int n_weights, int device, ttsb_tacotron2_t** out);
+void ttsb_tacotron2_destroy(ttsb_tacotron2_t* h);
+size_t ttsb_tacotron2_state_bytes(const ttsb_tacotron2_t* h, int B, int L, int max_steps);
+size_t ttsb_tacotron2_workspace_bytes(const ttsb_tacotron2_t* h, int B, int L, int T);
+int ttsb_tacotron2_encode(ttsb_tacotron2_t* h, const int64_t* d_tokens, const int32_t* d_lengths,
+                          const int64_t* d_speaker_ids, int B, int L, int max_steps, void* d_state,
+                          void* d_workspace, size_t workspace_bytes, void* stream);
+int ttsb_tacotron2_decode(ttsb_tacotron2_t* h, int B, int L, int max_steps, int step0, int n_steps,
+                          const uint8_t* d_masks, float gate_threshold, void* d_state, int* h_done_step,
+                          void* stream);
+int ttsb_tacotron2_finish(ttsb_tacotron2_t* h, int B, int L, int max_steps, int T, float* d_mel,
+                          int32_t* d_mel_lengths, float* d_alignments, void* d_mel_cl, void* d_state,
+                          void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Single conv site, for parity tests of the dense-contraction kernel in isolation.

@@ -64,6 +64,16 @@ _SIGNATURES = {
                                          c_void_p]),
     'ttsb_fastpitch_decode': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_size_t, c_void_p]),
+    'ttsb_tacotron2_create': (c_int, [ctypes.POINTER(TensorDesc), c_int, c_int, ctypes.POINTER(c_void_p)]),
+    'ttsb_tacotron2_destroy': (None, [c_void_p]),
+    'ttsb_tacotron2_state_bytes': (c_size_t, [c_void_p, c_int, c_int, c_int]),
+    'ttsb_tacotron2_workspace_bytes': (c_size_t, [c_void_p, c_int, c_int, c_int]),
+    'ttsb_tacotron2_encode': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                                      c_size_t, c_void_p]),
+    'ttsb_tacotron2_decode': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_float, c_void_p,
+                                      ctypes.POINTER(c_int), c_void_p]),
+    'ttsb_tacotron2_finish': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_size_t, c_void_p]),
     'ttsb_conv1d_create': (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                    ctypes.POINTER(c_void_p)]),
     'ttsb_conv1d_destroy': (None, [c_void_p]),

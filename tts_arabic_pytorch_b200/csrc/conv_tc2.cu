@@ -54,7 +54,7 @@ __device__ __forceinline__ void tl2_mark(const ConvTc2Args& a, int slot) {
     if (blockIdx.x < 256 && slot < 64) a.timeline[blockIdx.x * 128 + slot] = clock64();
 }
 
-template <int kTmemCols, int kMinBlocks>
+template <int kTmemCols, int kMinBlocks, bool kLean>
 __global__ void __launch_bounds__(192, kMinBlocks)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ ConvTc2Args args) {
     extern __shared__ uint8_t smem_raw[];
@@ -239,6 +239,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         const int n_base = ntile * args.n_tile;
         int tl_i = 0;
         const bool tl_on = threadIdx.x == 64;
+        uint8_t* stage = smem_stage + q * 2048;
+        // lean path: the first residual / MRF chunk of the NEXT work item is requested before this
+        // item's accumulator is waited for, so its latency hides behind a whole tile
+        LeanPrefetch pre_cur, pre_nxt;
+        if (kLean && first < args.n_work) {
+            const int b0 = first / args.groups_t;
+            const int w0 = (first - b0 * args.groups_t) * args.rpp * kTileM + q * 32;
+            RowIO io{stage, lane, min(32, max(0, args.T - w0))};
+            lean_prefetch(args.epi, io, static_cast<long>(b0) * args.T + w0, n_base, true, pre_cur);
+        }
         for (int idx = first; idx < args.n_work; idx += stride, ++tl_i) {
             const int b = idx / args.groups_t;
             const int tile0 = (idx - b * args.groups_t) * args.rpp;
@@ -263,12 +273,21 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         if (tl_on && tl_i < 7) tl2_mark(args, 8 + tl_i * 8 + 5);
                     }
                 };
-                // (a cross-tile register prefetch of the next tile's residual was tried in session 9: the
-                // extra 32 live registers pushed the 2-CTA variant into spills and cost 15-20 %)
-                long long* dbg = (tl_on && args.timeline != nullptr && blockIdx.x < 256 && tl_i < 7)
-                                     ? args.timeline + blockIdx.x * 128 + 64 + tl_i * 8 : nullptr;
-                run_epilogue(args.epi, acc, b, t, t < args.T, n_base, args.n_tile, wait_acc, drained,
-                             smem_stage + q * 2048, dbg);
+                if (kLean) {
+                    // next (item, r): either the next row tile of this item or the first of the next item
+                    const bool last_r = r == args.rpp - 1;
+                    const int nidx = last_r ? idx + stride : idx;
+                    const int nb = nidx / args.groups_t;
+                    const int nw0 = ((nidx - nb * args.groups_t) * args.rpp + (last_r ? 0 : r + 1)) * kTileM + q * 32;
+                    RowIO nio{stage, lane, min(32, max(0, args.T - nw0))};
+                    lean_prefetch(args.epi, nio, static_cast<long>(nb) * args.T + nw0, n_base, nidx < args.n_work, pre_nxt);
+                    run_epilogue_lean(args.epi, acc, b, t, n_base, args.n_tile, wait_acc, drained, stage, pre_cur);
+                    pre_cur = pre_nxt;
+                } else {
+                    long long* dbg = (tl_on && args.timeline != nullptr && blockIdx.x < 256 && tl_i < 7)
+                                         ? args.timeline + blockIdx.x * 128 + 64 + tl_i * 8 : nullptr;
+                    run_epilogue(args.epi, acc, b, t, t < args.T, n_base, args.n_tile, wait_acc, drained, stage, dbg);
+                }
             }
             if (tl_on && tl_i < 7) tl2_mark(args, 8 + tl_i * 8 + 6);
             if (buf) pf1 ^= 1; else pf0 ^= 1;
@@ -311,18 +330,28 @@ static int num_sms() {
     return n;
 }
 
-template <int kCols, int kMinBlocks>
-static int launch_two(const CUtensorMap& tm, const ConvTc2Args& a, int grid, size_t smem, cudaStream_t s) {
+template <int kCols, int kMinBlocks, bool kLean>
+static int launch_two_impl(const CUtensorMap& tm, const ConvTc2Args& a, int grid, size_t smem, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
-        TTSB_CHECK_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<kCols, kMinBlocks>,
+        TTSB_CHECK_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<kCols, kMinBlocks, kLean>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         configured = true;
     }
-    conv_tc2_kernel<kCols, kMinBlocks><<<grid, 192, smem, s>>>(tm, a);
+    conv_tc2_kernel<kCols, kMinBlocks, kLean><<<grid, 192, smem, s>>>(tm, a);
     count_launch();
     TTSB_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+static bool host_epi_is_lean(const EpiParams& e) {
+    return e.ln_g == nullptr && e.head_w == nullptr && e.out_f32_t == nullptr && e.out_f32 == nullptr &&
+           e.act_tanh == 0 && e.pre_ln_relu == 0;
+}
+template <int kCols, int kMinBlocks>
+static int launch_two(const CUtensorMap& tm, const ConvTc2Args& a, int grid, size_t smem, cudaStream_t s) {
+    return host_epi_is_lean(a.epi) ? launch_two_impl<kCols, kMinBlocks, true>(tm, a, grid, smem, s)
+                                   : launch_two_impl<kCols, kMinBlocks, false>(tm, a, grid, smem, s);
 }
 
 int conv_forward_tc2(const ConvLayer& L, const ConvRuntime& rt, const __half* in, int ld_in, int B,

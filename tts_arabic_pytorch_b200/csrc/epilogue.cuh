@@ -321,6 +321,86 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& e, const Acc& acc,
     }
     if (e.head_out && row_ok) e.head_out[row] = in_len ? head + e.head_b : 0.f;
 }
+// ------------------------------------------------------------------------------------------------
+// Lean epilogue: the vocoder's hot subset only (bias, residual, row mask, MRF accumulate, raw and
+// leaky-relu outputs). The general epilogue above costs ~1000 executed instructions per 32-column chunk
+// because every optional feature is a runtime branch; with ONE epilogue warp per SM sub-partition that
+// instruction stream — not memory — bounded the tile period (profiles/r01_s13_epilogue_detail.txt:
+// 3400 cycles of "math" per chunk). Here the feature set is fixed at compile time.
+// `pre` carries the first residual / MRF chunk requested while the previous tile was being finished.
+// ------------------------------------------------------------------------------------------------
+struct LeanPrefetch {
+    Chunk32 res, mrf;
+};
+__device__ __forceinline__ bool epi_is_lean(const EpiParams& e) {
+    return e.ln_g == nullptr && e.head_w == nullptr && e.out_f32_t == nullptr && e.out_f32 == nullptr &&
+           e.act_tanh == 0 && e.pre_ln_relu == 0;
+}
+__device__ __forceinline__ void lean_prefetch(const EpiParams& e, const RowIO& io, long row0, int n_base, bool on,
+                                              LeanPrefetch& p) {
+    const bool use_mrf = e.mrf_mode == MRF_ADD || e.mrf_mode == MRF_LAST;
+    io.request(e.residual + row0 * e.ld_res + n_base, e.ld_res, on && e.residual != nullptr, p.res);
+    io.request(e.mrf_buf + row0 * e.n_total + n_base, e.n_total, on && use_mrf, p.mrf);
+}
+
+template <class Acc, class WaitFn, class DrainFn>
+__device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc& acc, int b, int t, int n_base,
+                                                  int n_tile, WaitFn wait_acc, DrainFn acc_drained, uint8_t* stage,
+                                                  const LeanPrefetch& pre) {
+    const int lane = threadIdx.x & 31;
+    const int warp_row0 = t - lane;
+    const long row0 = static_cast<long>(b) * e.T + warp_row0;
+    const bool in_len = e.lens == nullptr || t < __ldg(e.lens + b) * e.len_mul;
+    RowIO io{stage, lane, min(32, max(0, e.T - warp_row0))};
+    const bool use_res = e.residual != nullptr;
+    const bool use_mrf = e.mrf_mode == MRF_ADD || e.mrf_mode == MRF_LAST;
+    const bool mrf_store = e.mrf_mode == MRF_FIRST || e.mrf_mode == MRF_ADD;
+    const __half* res_blk = e.residual + row0 * e.ld_res + n_base;
+    __half* mrf_blk = e.mrf_buf + row0 * e.n_total + n_base;
+    const float mscale = e.mrf_mode == MRF_NONE ? 1.f : e.mrf_scale;
+    const float slope = e.act_slope;
+
+    Chunk32 res_cur = pre.res, mrf_cur = pre.mrf;
+    wait_acc();
+    for (int c0 = 0; c0 < n_tile; c0 += 32) {
+        float v[32];
+        Chunk32 res_nxt, mrf_nxt;
+        const bool more = c0 + 32 < n_tile;
+        io.request(res_blk + c0 + 32, e.ld_res, use_res && more, res_nxt);
+        io.request(mrf_blk + c0 + 32, e.n_total, use_mrf && more, mrf_nxt);
+        if (use_res) io.to_row(res_cur);
+        if (use_mrf) io.to_row(mrf_cur);
+        __syncwarp();
+        acc.load(c0, v);
+        if (!more) acc_drained();
+        Chunk32 o_raw, o_act;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            float r[8], m[8], bs[8], x[8], a[8];
+            unpack8(res_cur.q[g], r);
+            unpack8(mrf_cur.q[g], m);
+            bias8(e.bias, n_base + c0 + g * 8, bs);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float y = v[g * 8 + j] + bs[j] + r[j];
+                y = in_len ? y : 0.f;
+                y = m[j] + y * mscale;
+                x[j] = y;
+                a[j] = y > 0.f ? y : y * slope;
+            }
+            o_raw.q[g] = pack8(x);
+            o_act.q[g] = pack8(a);
+        }
+        if (mrf_store) {
+            io.store(mrf_blk + c0, e.n_total, o_raw);
+        } else {
+            if (e.out_raw) io.store(e.out_raw + row0 * e.ld_raw + n_base + c0, e.ld_raw, o_raw);
+            if (e.out_act) io.store(e.out_act + row0 * e.ld_act + n_base + c0, e.ld_act, o_act);
+        }
+        res_cur = res_nxt;
+        mrf_cur = mrf_nxt;
+    }
+}
 #endif  // __CUDACC__
 
 }  // namespace ttsb

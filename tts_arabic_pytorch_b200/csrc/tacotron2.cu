@@ -12,6 +12,7 @@
 //             fp32 accumulation. The per-step host sync of the reference (torch.all(finished),
 //             torchaudio:850) is replaced by a device flag the caller polls every N steps.
 //   postnet   5 x [Conv1d k5 + BatchNorm(folded) (+tanh)] (tcgen05 conv kernel) + residual
+#include <algorithm>
 #include <cmath>
 #include "model_common.cuh"
 
