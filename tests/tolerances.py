@@ -16,3 +16,8 @@ WAV_LINF = 1e-2
 SCALAR_ABS = 1e-2
 E2E_WAV_REL_RMS = 2e-2
 E2E_WAV_LINF = 5e-2
+
+# Tacotron2 (fp16 weights, fp32 recurrent state, identical injected prenet masks; the decoder feeds its own
+# output back for every step, so the bound is looser than for the feed-forward FastPitch):
+T2_MEL_LINF = 5e-2
+T2_ALIGN_ABS = 2e-2

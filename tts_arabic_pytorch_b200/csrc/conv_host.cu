@@ -105,19 +105,22 @@ int conv_layer_create(ConvLayer& L, int cin_logical, int cin_stored, int n_total
         int want_res = w_all + std::min(L.n_chunks + 1, 2 * L.n_chunks) * panel <= bud ? 1 : 0;
         if (const char* e = getenv("TTSB_RESIDENT")) want_res = want_res && atoi(e) != 0;
         L.resident = want_res;
+        const int tmem_cap = L.occ2 == 3 ? 128 : (L.occ2 == 2 ? 256 : 512);
+        // row tiles per work item: light (resident) layers batch several 128-row tiles per item so the
+        // per-item barrier round trips and MMA issue latencies overlap across independent accumulators
         int rpp = 1;
         if (const char* e = getenv("TTSB_RPP")) {
             const int v = atoi(e);
-            if (!L.resident && L.occ2 == 1 && (v == 1 || v == 2 || v == 4) && v * n_tile <= 512) rpp = v;
+            if ((v == 1 || v == 2 || v == 4) && 2 * v * n_tile <= tmem_cap) rpp = v;
         }
         L.rpp = rpp;
-        const int tmem_cap = L.occ2 == 3 ? 128 : (L.occ2 == 2 ? 256 : 512);
         L.acc_bufs = 2 * rpp * n_tile <= tmem_cap ? 2 : 1;
         L.tmem_cols2 = 32;
         while (L.tmem_cols2 < L.acc_bufs * rpp * n_tile) L.tmem_cols2 *= 2;
         if (L.resident) {
             int as2 = static_cast<int>((bud - w_all) / panel);
-            as2 = std::min(as2, 4 * L.n_chunks);
+            as2 = std::min(as2, 4 * L.n_chunks * rpp);
+            TTSB_REQUIRE(as2 >= rpp * std::min(L.n_chunks, 2), "resident plan: panel ring too small for rpp");
             L.a_slots2 = as2;
             L.b_stages2 = 1;
             L.smem_bytes2 = 1024 + as2 * panel + w_all + (2 * as2 + 2 + 5) * 8 + 16 + 8192 + 256;
