@@ -54,7 +54,8 @@ __device__ __forceinline__ void tl2_mark(const ConvTc2Args& a, int slot) {
     if (blockIdx.x < 256 && slot < 64) a.timeline[blockIdx.x * 128 + slot] = clock64();
 }
 
-template <int kTmemCols, int kMinBlocks, bool kLean>
+// kEpi: 0 = general epilogue, 1 = lean (vocoder hot subset), 2 = lean + MRF accumulate
+template <int kTmemCols, int kMinBlocks, int kEpi>
 __global__ void __launch_bounds__(192, kMinBlocks)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ ConvTc2Args args) {
     extern __shared__ uint8_t smem_raw[];
@@ -242,7 +243,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         uint8_t* stage = smem_stage + q * 2048;
         // lean path: the first residual / MRF chunk of the NEXT work item is requested before this
         // item's accumulator is waited for, so its latency hides behind a whole tile
-        LeanPrefetch pre_cur, pre_nxt;
+        constexpr bool kLean = kEpi != 0;
+        constexpr bool kMrf = kEpi == 2;
+        LeanPrefetch<kMrf> pre_cur, pre_nxt;
         if (kLean && first < args.n_work) {
             const int b0 = first / args.groups_t;
             const int w0 = (first - b0 * args.groups_t) * args.rpp * kTileM + q * 32;
@@ -281,7 +284,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     const int nw0 = ((nidx - nb * args.groups_t) * args.rpp + (last_r ? 0 : r + 1)) * kTileM + q * 32;
                     RowIO nio{stage, lane, min(32, max(0, args.T - nw0))};
                     lean_prefetch(args.epi, nio, static_cast<long>(nb) * args.T + nw0, n_base, nidx < args.n_work, pre_nxt);
-                    run_epilogue_lean(args.epi, acc, b, t, n_base, args.n_tile, wait_acc, drained, stage, pre_cur);
+                    run_epilogue_lean<kMrf>(args.epi, acc, b, t, n_base, args.n_tile, wait_acc, drained, stage, pre_cur);
                     pre_cur = pre_nxt;
                 } else {
                     long long* dbg = (tl_on && args.timeline != nullptr && blockIdx.x < 256 && tl_i < 7)
@@ -330,15 +333,15 @@ static int num_sms() {
     return n;
 }
 
-template <int kCols, int kMinBlocks, bool kLean>
+template <int kCols, int kMinBlocks, int kEpi>
 static int launch_two_impl(const CUtensorMap& tm, const ConvTc2Args& a, int grid, size_t smem, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
-        TTSB_CHECK_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<kCols, kMinBlocks, kLean>,
+        TTSB_CHECK_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<kCols, kMinBlocks, kEpi>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         configured = true;
     }
-    conv_tc2_kernel<kCols, kMinBlocks, kLean><<<grid, 192, smem, s>>>(tm, a);
+    conv_tc2_kernel<kCols, kMinBlocks, kEpi><<<grid, 192, smem, s>>>(tm, a);
     count_launch();
     TTSB_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -350,8 +353,9 @@ static bool host_epi_is_lean(const EpiParams& e) {
 }
 template <int kCols, int kMinBlocks>
 static int launch_two(const CUtensorMap& tm, const ConvTc2Args& a, int grid, size_t smem, cudaStream_t s) {
-    return host_epi_is_lean(a.epi) ? launch_two_impl<kCols, kMinBlocks, true>(tm, a, grid, smem, s)
-                                   : launch_two_impl<kCols, kMinBlocks, false>(tm, a, grid, smem, s);
+    if (!host_epi_is_lean(a.epi)) return launch_two_impl<kCols, kMinBlocks, 0>(tm, a, grid, smem, s);
+    if (a.epi.mrf_mode == MRF_NONE) return launch_two_impl<kCols, kMinBlocks, 1>(tm, a, grid, smem, s);
+    return launch_two_impl<kCols, kMinBlocks, 2>(tm, a, grid, smem, s);
 }
 
 int conv_forward_tc2(const ConvLayer& L, const ConvRuntime& rt, const __half* in, int ld_in, int B,

@@ -96,6 +96,17 @@ struct Chunk32 {
 };
 __device__ __forceinline__ uint32_t wtile_off(int r, int u) { return r * 64 + ((u ^ ((r >> 1) & 3)) << 4); }
 
+// explicit shared-space accesses: through a generic pointer the compiler emits generic LD/ST (ST.E.128)
+// for the staging tile, which costs an address-space lookup per access
+__device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
+    return v;
+}
+
 struct RowIO {
     uint8_t* tile;      // this warp's 2 KB staging tile, or null -> direct per-row access
     int lane;
@@ -113,15 +124,16 @@ struct RowIO {
     // turn a requested block into this lane's own row (4 units of 8 columns)
     __device__ __forceinline__ void to_row(Chunk32& c) const {
         if (!tile) return;
+        const uint32_t base = smem_u32(tile);
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int id = i * 32 + lane;
-            *reinterpret_cast<uint4*>(tile + wtile_off(id >> 2, id & 3)) = c.q[i];
+            sts128(base + wtile_off(id >> 2, id & 3), c.q[i]);
         }
         __syncwarp();
 #pragma unroll
-        for (int u = 0; u < 4; ++u) c.q[u] = *reinterpret_cast<const uint4*>(tile + wtile_off(lane, u));
+        for (int u = 0; u < 4; ++u) c.q[u] = lds128(base + wtile_off(lane, u));
     }
     // write this lane's own row (4 units) of a [32 x 32] block
     __device__ __forceinline__ void store(__half* blk, long ld, const Chunk32& own) const {
@@ -132,15 +144,16 @@ struct RowIO {
             }
             return;
         }
+        const uint32_t base = smem_u32(tile);
         __syncwarp();
 #pragma unroll
-        for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(tile + wtile_off(lane, u)) = own.q[u];
+        for (int u = 0; u < 4; ++u) sts128(base + wtile_off(lane, u), own.q[u]);
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int id = i * 32 + lane;
             const int r = id >> 2, u = id & 3;
-            const uint4 v = *reinterpret_cast<const uint4*>(tile + wtile_off(r, u));
+            const uint4 v = lds128(base + wtile_off(r, u));
             if (r < rows_valid) *reinterpret_cast<uint4*>(blk + r * ld + u * 8) = v;
         }
     }
@@ -329,47 +342,50 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& e, const Acc& acc,
 // 3400 cycles of "math" per chunk). Here the feature set is fixed at compile time.
 // `pre` carries the first residual / MRF chunk requested while the previous tile was being finished.
 // ------------------------------------------------------------------------------------------------
+template <bool kMrf>
 struct LeanPrefetch {
-    Chunk32 res, mrf;
+    Chunk32 res;
+    Chunk32 mrf;   // only live when kMrf (otherwise never touched, so it costs no registers)
 };
-__device__ __forceinline__ bool epi_is_lean(const EpiParams& e) {
-    return e.ln_g == nullptr && e.head_w == nullptr && e.out_f32_t == nullptr && e.out_f32 == nullptr &&
-           e.act_tanh == 0 && e.pre_ln_relu == 0;
-}
+template <bool kMrf>
 __device__ __forceinline__ void lean_prefetch(const EpiParams& e, const RowIO& io, long row0, int n_base, bool on,
-                                              LeanPrefetch& p) {
-    const bool use_mrf = e.mrf_mode == MRF_ADD || e.mrf_mode == MRF_LAST;
+                                              LeanPrefetch<kMrf>& p) {
     io.request(e.residual + row0 * e.ld_res + n_base, e.ld_res, on && e.residual != nullptr, p.res);
-    io.request(e.mrf_buf + row0 * e.n_total + n_base, e.n_total, on && use_mrf, p.mrf);
+    if (kMrf) {
+        const bool use_mrf = e.mrf_mode == MRF_ADD || e.mrf_mode == MRF_LAST;
+        io.request(e.mrf_buf + row0 * e.n_total + n_base, e.n_total, on && use_mrf, p.mrf);
+    }
 }
 
-template <class Acc, class WaitFn, class DrainFn>
+// kMrf = false: mrf_mode == MRF_NONE is guaranteed by the caller.
+template <bool kMrf, class Acc, class WaitFn, class DrainFn>
 __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc& acc, int b, int t, int n_base,
                                                   int n_tile, WaitFn wait_acc, DrainFn acc_drained, uint8_t* stage,
-                                                  const LeanPrefetch& pre) {
+                                                  const LeanPrefetch<kMrf>& pre) {
     const int lane = threadIdx.x & 31;
     const int warp_row0 = t - lane;
     const long row0 = static_cast<long>(b) * e.T + warp_row0;
     const bool in_len = e.lens == nullptr || t < __ldg(e.lens + b) * e.len_mul;
     RowIO io{stage, lane, min(32, max(0, e.T - warp_row0))};
     const bool use_res = e.residual != nullptr;
-    const bool use_mrf = e.mrf_mode == MRF_ADD || e.mrf_mode == MRF_LAST;
-    const bool mrf_store = e.mrf_mode == MRF_FIRST || e.mrf_mode == MRF_ADD;
+    const bool use_mrf = kMrf && (e.mrf_mode == MRF_ADD || e.mrf_mode == MRF_LAST);
+    const bool mrf_store = kMrf && (e.mrf_mode == MRF_FIRST || e.mrf_mode == MRF_ADD);
     const __half* res_blk = e.residual + row0 * e.ld_res + n_base;
     __half* mrf_blk = e.mrf_buf + row0 * e.n_total + n_base;
-    const float mscale = e.mrf_mode == MRF_NONE ? 1.f : e.mrf_scale;
+    const float mscale = kMrf ? e.mrf_scale : 1.f;
     const float slope = e.act_slope;
 
-    Chunk32 res_cur = pre.res, mrf_cur = pre.mrf;
+    Chunk32 res_cur = pre.res, mrf_cur;
+    if (kMrf) mrf_cur = pre.mrf;
     wait_acc();
     for (int c0 = 0; c0 < n_tile; c0 += 32) {
         float v[32];
         Chunk32 res_nxt, mrf_nxt;
         const bool more = c0 + 32 < n_tile;
         io.request(res_blk + c0 + 32, e.ld_res, use_res && more, res_nxt);
-        io.request(mrf_blk + c0 + 32, e.n_total, use_mrf && more, mrf_nxt);
+        if (kMrf) io.request(mrf_blk + c0 + 32, e.n_total, use_mrf && more, mrf_nxt);
         if (use_res) io.to_row(res_cur);
-        if (use_mrf) io.to_row(mrf_cur);
+        if (kMrf && use_mrf) io.to_row(mrf_cur);
         __syncwarp();
         acc.load(c0, v);
         if (!more) acc_drained();
@@ -378,13 +394,13 @@ __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc&
         for (int g = 0; g < 4; ++g) {
             float r[8], m[8], bs[8], x[8], a[8];
             unpack8(res_cur.q[g], r);
-            unpack8(mrf_cur.q[g], m);
+            if (kMrf) unpack8(mrf_cur.q[g], m);
             bias8(e.bias, n_base + c0 + g * 8, bs);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 float y = v[g * 8 + j] + bs[j] + r[j];
                 y = in_len ? y : 0.f;
-                y = m[j] + y * mscale;
+                if (kMrf) y = m[j] + y * mscale;
                 x[j] = y;
                 a[j] = y > 0.f ? y : y * slope;
             }
@@ -398,7 +414,7 @@ __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc&
             if (e.out_act) io.store(e.out_act + row0 * e.ld_act + n_base + c0, e.ld_act, o_act);
         }
         res_cur = res_nxt;
-        mrf_cur = mrf_nxt;
+        if (kMrf) mrf_cur = mrf_nxt;
     }
 }
 #endif  // __CUDACC__
