@@ -80,3 +80,24 @@ def test_speed_changes_length(tts_model):
     n1 = tts_model.tts(LINES[0], denoise=0, speed=1.0).numel()
     n2 = tts_model.tts(LINES[0], denoise=0, speed=2.0).numel()
     assert n2 == n1 // 2      # const-4 durations: round(4/2) = 2 frames per token
+
+
+def test_tacotron2wave_api(tmp_path_factory):
+    """Tacotron2Wave.tts (models/tacotron2/networks.py:347-426): text in, 1-D fp32 CPU waveforms out, mel
+    post-processing (separator insertion + alignment-based truncation) and speed resize on the way."""
+    import os
+    from tts_arabic_pytorch_b200.models.tacotron2 import Tacotron2Wave
+    d = tmp_path_factory.mktemp('ckpt_t2')
+    fp, hg, cj = synth.write_checkpoints(str(d), seed=1234)
+    m = Tacotron2Wave(os.path.join(str(d), 'tacotron2.pth'), vocoder_sd=hg, vocoder_config=cj, arabic_in=False).cuda()
+    m.model.decoder_max_step = 40          # synthetic weights never raise the stop gate
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        w = m.tts(LINES[0], denoise=0)
+        ws = m.tts(LINES[:2], batch_size=2, denoise=0, speed=1.25)
+        mel = m.model.ttmel(LINES[1], postprocess_mel=False)
+    assert isinstance(w, torch.Tensor) and w.dim() == 1 and w.device.type == 'cpu' and w.numel() % 256 == 0
+    assert bool(torch.isfinite(w).all()) and float(w.abs().max()) <= 1.0
+    assert len(ws) == 2 and all(x.dim() == 1 and x.numel() % 256 == 0 for x in ws)
+    assert mel.shape == (80, 40) and mel.device.type == 'cuda'

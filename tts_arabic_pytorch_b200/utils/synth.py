@@ -258,4 +258,6 @@ def write_checkpoints(directory, seed=1234, dur_mode='const4'):
     torch.save({'generator': hifigan_state_dict(seed + 1)}, hg)
     with open(cj, 'w') as f:
         json.dump(HIFIGAN_CONFIG, f)
+    # Tacotron2 checkpoint format: {'model': state_dict} (models/tacotron2/networks.py:85-98)
+    torch.save({'model': tacotron2_state_dict(seed + 2)}, os.path.join(directory, 'tacotron2.pth'))
     return fp, hg, cj
