@@ -13,6 +13,9 @@ _ALIASES = {
     'models.fastpitch.networks': 'tts_arabic_pytorch_b200.models.fastpitch.networks',
     'models.fastpitch.fastpitch': 'tts_arabic_pytorch_b200.models.fastpitch.fastpitch',
     'models.fastpitch.fastpitch.model': 'tts_arabic_pytorch_b200.models.fastpitch.fastpitch.model',
+    'models.tacotron2': 'tts_arabic_pytorch_b200.models.tacotron2',
+    'models.tacotron2.networks': 'tts_arabic_pytorch_b200.models.tacotron2.networks',
+    'models.tacotron2.tacotron2_ms': 'tts_arabic_pytorch_b200.models.tacotron2.tacotron2_ms',
     'vocoder': 'tts_arabic_pytorch_b200.vocoder',
     'vocoder.hifigan': 'tts_arabic_pytorch_b200.vocoder.hifigan',
     'vocoder.hifigan.models': 'tts_arabic_pytorch_b200.vocoder.hifigan.models',
