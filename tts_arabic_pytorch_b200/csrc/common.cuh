@@ -147,6 +147,24 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
         : "memory");
 }
 
+// 1-D bulk copy delivered to the same CTA-relative offset (data and mbarrier) in every CTA of `cta_mask`
+__device__ __forceinline__ void bulk_load_1d_multicast(void* smem_dst, const void* gsrc, uint32_t bytes,
+                                                       uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ----------------------------------------------------------------------------------------------
@@ -183,6 +201,12 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                  ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// same, arriving on the barrier at this CTA-relative offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask)
                  : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets TMEM lane (base_lane + i).

@@ -29,6 +29,7 @@ struct ConvTc2Args {
     int groups_t;      // work items per utterance = ceil(tiles_t / rpp)
     int n_work;        // B * groups_t
     int resident;      // 1: all weight tiles of this N tile stay in smem for the CTA's lifetime
+    int cluster;       // 1, or 2: CTA pairs share every streamed weight tile (each loads half, multicast to both)
     int n_tiles_n;
     int n_chunks, n_taps;
     int chunk_k;       // 64 or 32
@@ -82,15 +83,23 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int ntile = blockIdx.x % args.n_tiles_n;
-    const int first = blockIdx.x / args.n_tiles_n;
-    const int stride = gridDim.x / args.n_tiles_n;
+    // Work items: cluster `cid` owns N tile cid % n_tiles_n and walks item groups p = first, first+stride, ...;
+    // CTA `crank` of the cluster takes item p*csize + crank (a missing last item is a dummy: all rows out
+    // of range). Both CTAs of a pair therefore make exactly the same number of weight passes.
+    const int csize = args.cluster;
+    const int crank = csize == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+    const int cid = blockIdx.x / csize;
+    const int ntile = cid % args.n_tiles_n;
+    const int first = cid / args.n_tiles_n;
+    const int stride = (gridDim.x / csize) / args.n_tiles_n;
+    const int n_groups = (args.n_work + csize - 1) / csize;
+    const uint16_t cmask = static_cast<uint16_t>((1u << csize) - 1u);
 
     if (warp == 0 && elect_one()) {
         tl2_mark(args, 0);
         tma_prefetch_desc(&tmap_a);
         for (int i = 0; i < args.a_slots; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
-        for (int i = 0; i < args.b_stages; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
+        for (int i = 0; i < args.b_stages; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], csize); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
         mbar_init(w_full, 1);
         fence_mbar_init();
@@ -98,6 +107,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
     tc_fence_before();
     __syncthreads();
+    if (csize == 2) cluster_sync_all();   // peer barriers must be initialised before any multicast / remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) tl2_mark(args, 1);
@@ -115,9 +125,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     bulk_load_1d(smem_b + i * btile_bytes, wtiles + static_cast<size_t>(i) * btile_bytes, btile_bytes, w_full);
             }
             int item = 0;
-            for (int idx = first; idx < args.n_work; idx += stride, ++item) {
-                const int b = idx / args.groups_t;
-                const int tile0 = (idx - b * args.groups_t) * args.rpp;
+            const int half_bytes = btile_bytes / 2;
+            for (int p = first; p < n_groups; p += stride, ++item) {
+                const int idx = p * csize + crank;
+                const bool valid = idx < args.n_work;
+                const int b = valid ? idx / args.groups_t : 0;
+                const int tile0 = valid ? (idx - b * args.groups_t) * args.rpp : args.groups_t * args.rpp;
                 const uint8_t* wp = wtiles;
                 for (int c = 0; c < args.n_chunks; ++c) {
                     for (int r = 0; r < args.rpp; ++r) {
@@ -132,7 +145,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         for (int tap = 0; tap < args.n_taps; ++tap) {
                             mbar_wait(&empty_b[sb], pb, args.err_flag, 202);
                             mbar_expect_tx(&full_b[sb], btile_bytes);
-                            bulk_load_1d(smem_b + sb * btile_bytes, wp, btile_bytes, &full_b[sb]);
+                            if (csize == 2)
+                                bulk_load_1d_multicast(smem_b + sb * btile_bytes + crank * half_bytes, wp + crank * half_bytes,
+                                                       half_bytes, &full_b[sb], cmask);
+                            else
+                                bulk_load_1d(smem_b + sb * btile_bytes, wp, btile_bytes, &full_b[sb]);
                             wp += btile_bytes;
                             if (++sb == args.b_stages) { sb = 0; pb ^= 1; }
                         }
@@ -169,7 +186,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 tc_fence_after();
             }
             int tl_i = 0;
-            for (int idx = first; idx < args.n_work; idx += stride, ++tl_i) {
+            for (int p = first; p < n_groups; p += stride, ++tl_i) {
                 mbar_wait(&tmem_empty[buf], buf ? pe1 : pe0, args.err_flag, 203);
                 tc_fence_after();
                 if (tl_i < 7) tl2_mark(args, 8 + tl_i * 8 + 0);
@@ -218,7 +235,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         }
                         accumulate = 1;
                         if (!args.resident) {
-                            umma_commit(&empty_b[sb]);
+                            if (csize == 2) umma_commit_multicast(&empty_b[sb], cmask);
+                            else umma_commit(&empty_b[sb]);
                             if (++sb == args.b_stages) { sb = 0; pb ^= 1; }
                         }
                     }
@@ -246,15 +264,19 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         constexpr bool kLean = kEpi != 0;
         constexpr bool kMrf = kEpi == 2;
         LeanPrefetch<kMrf> pre_cur, pre_nxt;
-        if (kLean && first < args.n_work) {
-            const int b0 = first / args.groups_t;
-            const int w0 = (first - b0 * args.groups_t) * args.rpp * kTileM + q * 32;
+        if (kLean && first < n_groups) {
+            const int idx0 = first * csize + crank;
+            const bool v0 = idx0 < args.n_work;
+            const int b0 = v0 ? idx0 / args.groups_t : 0;
+            const int w0 = (v0 ? (idx0 - b0 * args.groups_t) * args.rpp : args.groups_t * args.rpp) * kTileM + q * 32;
             RowIO io{stage, lane, min(32, max(0, args.T - w0))};
-            lean_prefetch(args.epi, io, static_cast<long>(b0) * args.T + w0, n_base, true, pre_cur);
+            lean_prefetch(args.epi, io, static_cast<long>(b0) * args.T + w0, n_base, v0, pre_cur);
         }
-        for (int idx = first; idx < args.n_work; idx += stride, ++tl_i) {
-            const int b = idx / args.groups_t;
-            const int tile0 = (idx - b * args.groups_t) * args.rpp;
+        for (int p = first; p < n_groups; p += stride, ++tl_i) {
+            const int idx = p * csize + crank;
+            const bool valid = idx < args.n_work;
+            const int b = valid ? idx / args.groups_t : 0;
+            const int tile0 = valid ? (idx - b * args.groups_t) * args.rpp : args.groups_t * args.rpp;
             const uint32_t par = buf ? pf1 : pf0;
             if (tl_on && tl_i < 7) tl2_mark(args, 8 + tl_i * 8 + 3);
             for (int r = 0; r < args.rpp; ++r) {
@@ -279,11 +301,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 if (kLean) {
                     // next (item, r): either the next row tile of this item or the first of the next item
                     const bool last_r = r == args.rpp - 1;
-                    const int nidx = last_r ? idx + stride : idx;
-                    const int nb = nidx / args.groups_t;
-                    const int nw0 = ((nidx - nb * args.groups_t) * args.rpp + (last_r ? 0 : r + 1)) * kTileM + q * 32;
+                    const int nidx = last_r ? (p + stride) * csize + crank : idx;
+                    const bool nvalid = nidx < args.n_work && (!last_r || p + stride < n_groups);
+                    const int nb = nvalid ? nidx / args.groups_t : 0;
+                    const int nw0 = ((nvalid ? (nidx - nb * args.groups_t) * args.rpp : args.groups_t * args.rpp) +
+                                     (last_r ? 0 : r + 1)) * kTileM + q * 32;
                     RowIO nio{stage, lane, min(32, max(0, args.T - nw0))};
-                    lean_prefetch(args.epi, nio, static_cast<long>(nb) * args.T + nw0, n_base, nidx < args.n_work, pre_nxt);
+                    lean_prefetch(args.epi, nio, static_cast<long>(nb) * args.T + nw0, n_base, nvalid, pre_nxt);
                     run_epilogue_lean<kMrf>(args.epi, acc, b, t, n_base, args.n_tile, wait_acc, drained, stage, pre_cur);
                     pre_cur = pre_nxt;
                 } else {
@@ -299,6 +323,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     }
     tc_fence_before();
     __syncthreads();
+    if (csize == 2) cluster_sync_all();   // no CTA may exit while its peer can still multicast into it
     if (warp == 2) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
@@ -341,7 +366,23 @@ static int launch_two_impl(const CUtensorMap& tm, const ConvTc2Args& a, int grid
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         configured = true;
     }
-    conv_tc2_kernel<kCols, kMinBlocks, kEpi><<<grid, 192, smem, s>>>(tm, a);
+    if (a.cluster == 2) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(192);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        TTSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<kCols, kMinBlocks, kEpi>, tm, a));
+    } else {
+        conv_tc2_kernel<kCols, kMinBlocks, kEpi><<<grid, 192, smem, s>>>(tm, a);
+    }
     count_launch();
     TTSB_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -427,12 +468,17 @@ int conv_forward_tc2(const ConvLayer& L, const ConvRuntime& rt, const __half* in
     a.w = L.w_packed; a.err_flag = rt.err_flag; a.epi = epi;
     a.timeline = rt.timeline;
 
-    // persistent grid: `occ` CTAs per SM, a multiple of the number of N tiles
+    // CTA pairs share streamed weight tiles through TMA multicast (halves the L2->SM weight traffic that
+    // bounds the C >= 128 layers); needs at least two work items per N tile
+    static const int want_cluster = getenv("TTSB_CLUSTER") ? atoi(getenv("TTSB_CLUSTER")) : 2;
+    a.cluster = (!L.resident && want_cluster == 2 && a.n_work >= 2 && (L.n_tile / 2) % 8 == 0) ? 2 : 1;
+    // persistent grid: `occ` CTAs per SM, a multiple of (cluster size x number of N tiles)
     int ctas = num_sms() * L.occ2;
     const long total = static_cast<long>(a.n_work) * a.n_tiles_n;
     if (ctas > total) ctas = static_cast<int>(total);
-    ctas = (ctas / a.n_tiles_n) * a.n_tiles_n;
-    if (ctas < a.n_tiles_n) ctas = a.n_tiles_n;
+    const int unit = a.n_tiles_n * a.cluster;
+    ctas = (ctas / unit) * unit;
+    if (ctas < unit) ctas = unit;
     // the register cap follows the planned CTAs per SM (1: 255, 2: 168, 3: 112 registers per thread)
     if (L.occ2 >= 3) {
         switch (L.tmem_cols2) {
