@@ -182,6 +182,20 @@ int ttsb_conv1d_cin_pad(const ttsb_conv1d_t* h);
 int ttsb_conv1d_forward(ttsb_conv1d_t* h, const void* d_in, int B, int T, const void* d_residual,
                         float act_slope, const int32_t* d_lens, void* d_out, void* stream);
 
+/* Op-level entry for one fused ResBlock1 step (vocoder/hifigan/models.py:46-53, one (c1, c2) iteration):
+ *   out = x + conv2(lrelu(conv1(lrelu(x)) + b1)) + b2,  conv1 = Conv1d(C, C, k, dilation=d), conv2 = Conv1d(C, C, k)
+ * as ONE kernel launch (csrc/conv_pair.cu). w1/w2: [C, C, k] fp32 host, b1/b2: [C]. d_x/d_out: [B, T, C] fp16
+ * channel-last, rows >= d_lens[b] (optional) are zero padding on both sides of the step.
+ * ttsb_convpair_plan fills {ok, rows per tile, x slots, t slots, w2 resident, w2 ring stages, TMEM columns, smem bytes};
+ * ok = 0 means the shape has no fused plan (the generator then runs the two convs as separate launches). */
+typedef struct ttsb_convpair ttsb_convpair_t;
+int ttsb_convpair_create(int channels, int ksize, int dilation, const float* h_w1, const float* h_b1,
+                         const float* h_w2, const float* h_b2, int device, ttsb_convpair_t** out);
+void ttsb_convpair_destroy(ttsb_convpair_t* h);
+int ttsb_convpair_plan(const ttsb_convpair_t* h, int* out8);
+int ttsb_convpair_forward(ttsb_convpair_t* h, const void* d_x, int B, int T, const int32_t* d_lens, float slope,
+                          void* d_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

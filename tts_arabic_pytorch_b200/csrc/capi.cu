@@ -9,6 +9,11 @@ struct ttsb_conv1d {
     int kind = 0, cin = 0, cout = 0, stride = 1;
 };
 
+struct ttsb_convpair {
+    ConvLayer c1, c2;
+    ConvPairPlan plan;
+};
+
 extern "C" {
 
 const char* ttsb_last_error(void) { return get_last_error(); }
@@ -88,6 +93,46 @@ int ttsb_conv1d_forward(ttsb_conv1d_t* h, const void* d_in, int B, int T, const 
     }
     return conv_forward(h->layer, rt, static_cast<const __half*>(d_in), h->layer.cin, B, T, e,
                         static_cast<cudaStream_t>(stream));
+}
+
+int ttsb_convpair_create(int channels, int ksize, int dilation, const float* h_w1, const float* h_b1,
+                         const float* h_w2, const float* h_b2, int device, ttsb_convpair_t** out) {
+    TTSB_REQUIRE(h_w1 && h_b1 && h_w2 && h_b2 && out, "null argument");
+    TTSB_CHECK_CUDA(cudaSetDevice(device));
+    ttsb_convpair* h = new ttsb_convpair();
+    int st = make_conv1d_layer(h->c1, h_w1, h_b1, channels, channels, ksize, dilation, channels, 0);
+    if (st == 0) st = make_conv1d_layer(h->c2, h_w2, h_b2, channels, channels, ksize, 1, channels, 0);
+    if (st != 0) { ttsb_convpair_destroy(h); return st; }
+    h->plan = conv_pair_plan(h->c1, h->c2);
+    *out = h;
+    return 0;
+}
+void ttsb_convpair_destroy(ttsb_convpair_t* h) {
+    if (!h) return;
+    conv_layer_destroy(h->c1);
+    conv_layer_destroy(h->c2);
+    delete h;
+}
+int ttsb_convpair_plan(const ttsb_convpair_t* h, int* out8) {
+    TTSB_REQUIRE(h && out8, "null argument");
+    const ConvPairPlan& p = h->plan;
+    const int v[8] = {p.ok, p.m_out, p.x_slots, p.tt_slots, p.w2_resident, p.b_stages, p.tmem_cols,
+                      static_cast<int>(p.smem_bytes)};
+    for (int i = 0; i < 8; ++i) out8[i] = v[i];
+    return 0;
+}
+int ttsb_convpair_forward(ttsb_convpair_t* h, const void* d_x, int B, int T, const int32_t* d_lens, float slope,
+                          void* d_out, void* stream) {
+    TTSB_REQUIRE(h && d_x && d_out, "null argument");
+    TTSB_REQUIRE(h->plan.ok, "this (channels, ksize, dilation) has no fused plan");
+    ConvRuntime rt;
+    TTSB_PROPAGATE(get_conv_runtime(0, rt));
+    EpiParams e;
+    e.lens = d_lens; e.len_mul = 1;
+    e.out_raw = static_cast<__half*>(d_out); e.ld_raw = h->plan.C;
+    e.act_slope = slope;
+    return conv_pair_forward(h->c1, h->c2, h->plan, rt, static_cast<const __half*>(d_x), B, T, slope, e,
+                             static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

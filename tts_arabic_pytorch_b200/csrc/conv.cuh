@@ -69,4 +69,27 @@ struct ConvRuntime {
 int conv_forward(const ConvLayer& L, const ConvRuntime& rt, const __half* in, int ld_in, int B,
                  int T, EpiParams epi, cudaStream_t stream);
 
+// shared by the tcgen05 kernels (defined in conv_tc2.cu)
+int get_act_tensor_map(const __half* in, int ld_in, int B, int T, int cin, int chunk_k, int rows_panel,
+                       const CUtensorMap** out);
+int num_sms();
+
+// ------------------------------------------------------------------------------------------------
+// Fused ResBlock1 step (conv_pair.cu):  out = x + conv2(lrelu(conv1(lrelu(x)) + b1)) + b2
+// (vocoder/hifigan/models.py:46-53: one (c1, c2) iteration of ResBlock1.forward) in ONE launch;
+// the intermediate never leaves the SM. L1 = dilated conv, L2 = dilation-1 conv, same C and k.
+// ------------------------------------------------------------------------------------------------
+struct ConvPairPlan {
+    int ok = 0;
+    int C = 0, m_out = 0, h2 = 0, dil = 1, rows_panel = 0, tt_rows = 0;
+    int x_slots = 0, tt_slots = 0, w2_resident = 0, b_stages = 0, tmem_cols = 0;
+    size_t smem_bytes = 0;
+};
+// ok = 0 when the pair does not fit the fused kernel (caller falls back to two conv_forward launches)
+ConvPairPlan conv_pair_plan(const ConvLayer& L1, const ConvLayer& L2);
+// x: [B, T, C] raw (NOT pre-activated) input, also the residual. epi: bias/T/n_total/residual are
+// filled here; the caller sets lens/len_mul, out_raw or mrf_* (+ out_act), act_slope.
+int conv_pair_forward(const ConvLayer& L1, const ConvLayer& L2, const ConvPairPlan& plan, const ConvRuntime& rt,
+                      const __half* x, int B, int T, float slope, EpiParams epi, cudaStream_t stream);
+
 }  // namespace ttsb

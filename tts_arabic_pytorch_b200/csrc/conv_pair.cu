@@ -1,0 +1,524 @@
+// conv_pair: one ResBlock1 step  x' = x + conv2(lrelu(conv1(lrelu(x)) + b1)) + b2  in ONE launch
+// (vocoder/hifigan/models.py:46-53, one (c1, c2) iteration; conv1 dilated, conv2 dilation 1).
+//
+// Why: with one launch per conv (conv_tc2) a pair moves six activation tensors through HBM
+// (lrelu(x) in, t out, t in, x in, x' out, lrelu(x') out). For C <= 64 that traffic — not the
+// tensor pipe — bounds the layer (profiles/r01_s18_launches_b64.csv: the C=32/64 stages take as long
+// as the C=128 stage with 1/4..1/2 of its FLOPs). Here the pair reads x once and writes x' once:
+//
+//   TMA      x panel (128 + 2*h1 rows, raw)                          -> smem X slot
+//   warps    lrelu in place (half2 max(x, 0.1x))                      -> the A operand of conv1
+//   tcgen05  conv1: k row-shifted views of the panel x W1 (resident)  -> TMEM acc1
+//   warps    acc1 + b1 -> lrelu -> row mask -> fp16, written in the UMMA swizzled layout
+//                                                                     -> smem TT panel (never leaves the SM)
+//   tcgen05  conv2: k row-shifted views of TT x W2                    -> TMEM acc2
+//   warps    acc2 + b2 + x (re-read from L2) -> mask -> x' (or the MRF accumulate / stage output)
+//
+// A tile owns m_out = 128 - 2*h2 output rows: conv1 is evaluated on 128 rows (the tile plus conv2's
+// halo), conv2 on 128 rows of which the last 2*h2 are discarded (they read beyond the TT rows).
+// MMA issue order is conv1(i+1) before conv2(i), so the tensor pipe works on the next tile while the
+// mid epilogue turns acc1(i) into TT(i); both accumulators are double-buffered in TMEM (4*C columns).
+//
+// Warp roles (384 threads): 0 TMA producer, 1 MMA issuer, 2-3 lrelu transform, 4-7 mid epilogue,
+// 8-11 final epilogue (the lean epilogue of epilogue.cuh).
+#include <cstdlib>
+#include "conv.cuh"
+
+namespace ttsb {
+
+constexpr int kPairThreads = 384;
+constexpr int kPairMaxX = 8;
+constexpr int kPairMaxB = 8;
+
+struct ConvPairArgs {
+    int B, T;
+    int m_out;        // output rows owned by a tile
+    int tiles_t;      // ceil(T / m_out)
+    int n_work;       // B * tiles_t
+    int C, chunk_k, n_chunks, n_taps;
+    int h2;           // (k - 1) / 2
+    int dil;          // conv1 dilation (tap step in rows); h1 = h2 * dil
+    int rows_panel;   // x panel rows per chunk (multiple of 8, >= 128 + 2*h1)
+    int tt_rows;      // TT panel rows per chunk (multiple of 8, >= 128 + 2*h2)
+    int x_slots, tt_slots;
+    int w2_resident, b_stages;
+    const __half* w1;
+    const __half* w2;
+    const float* bias1;
+    float slope;
+    int* err_flag;
+    long long* timeline;   // debug (tools/timeline_pair.py): 128 clock64() slots per CTA for the first 256 CTAs, or null
+    EpiParams epi;    // final epilogue: bias = b2, residual = x, outputs
+};
+
+// slot = 8 + item*16 + k for the CTA's first 7 items; k: 0 x issued, 1 x landed (transform), 2 transform done,
+// 3 conv1 operands ready, 4 conv1 issued, 5 conv2 operands ready, 6 conv2 issued, 7 acc1 seen (mid), 8 TT slot free,
+// 9 mid done, 10 final epilogue starts waiting, 11 acc2 seen, 12 final done
+__device__ __forceinline__ void tlp_mark(const ConvPairArgs& a, int item, int k) {
+    if (a.timeline == nullptr) return;
+    if (blockIdx.x < 256 && item < 7) a.timeline[blockIdx.x * 128 + 8 + item * 16 + k] = clock64();
+}
+
+__device__ __forceinline__ uint32_t lrelu_h2(uint32_t u, __half2 slope2) {
+    __half2 x = *reinterpret_cast<__half2*>(&u);
+    __half2 y = __hmax2(x, __hmul2(x, slope2));
+    return *reinterpret_cast<uint32_t*>(&y);
+}
+
+template <int kTmemCols, int kEpi>
+__global__ void __launch_bounds__(kPairThreads, 1)
+conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ ConvPairArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_u32 = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw_u32 & 1023u)) & 1023u);
+
+    const int C = args.C;
+    const int row_bytes = args.chunk_k * 2;
+    const int panel_bytes = args.rows_panel * row_bytes;
+    const int xslot_bytes = args.n_chunks * panel_bytes;
+    const int ttp_bytes = args.tt_rows * row_bytes;
+    const int ttslot_bytes = args.n_chunks * ttp_bytes;
+    const int btile_bytes = C * row_bytes;
+    const int n_btiles = args.n_chunks * args.n_taps;
+    const int h1 = args.h2 * args.dil;
+
+    uint8_t* smem_x = smem;
+    uint8_t* smem_tt = smem_x + args.x_slots * xslot_bytes;
+    uint8_t* smem_w1 = smem_tt + args.tt_slots * ttslot_bytes;
+    uint8_t* smem_w2 = smem_w1 + n_btiles * btile_bytes;
+    uint8_t* smem_end = smem_w2 + (args.w2_resident ? n_btiles : args.b_stages) * btile_bytes;
+    uint64_t* x_full = reinterpret_cast<uint64_t*>(smem_end);
+    uint64_t* xl_full = x_full + kPairMaxX;
+    uint64_t* x_empty = xl_full + kPairMaxX;
+    uint64_t* full_b = x_empty + kPairMaxX;
+    uint64_t* empty_b = full_b + kPairMaxB;
+    uint64_t* tt_full = empty_b + kPairMaxB;     // [2]
+    uint64_t* tt_empty = tt_full + 2;            // [2]
+    uint64_t* acc1_full = tt_empty + 2;          // [2]
+    uint64_t* acc1_empty = acc1_full + 2;        // [2]
+    uint64_t* acc2_full = acc1_empty + 2;        // [2]
+    uint64_t* acc2_empty = acc2_full + 2;        // [2]
+    uint64_t* w_full = acc2_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+    uint8_t* smem_stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 127) & ~static_cast<uintptr_t>(127));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int grid = gridDim.x;
+
+    if (warp == 0 && elect_one()) {
+        if (args.timeline != nullptr && blockIdx.x < 256) args.timeline[blockIdx.x * 128] = clock64();
+        tma_prefetch_desc(&tmap_x);
+        for (int i = 0; i < args.x_slots; ++i) { mbar_init(&x_full[i], 1); mbar_init(&xl_full[i], 2); mbar_init(&x_empty[i], 1); }
+        for (int i = 0; i < args.b_stages; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tt_full[i], 4); mbar_init(&tt_empty[i], 1);
+            mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], 4);
+            mbar_init(&acc2_full[i], 1); mbar_init(&acc2_empty[i], 4);
+        }
+        mbar_init(w_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
+    // rows [128, tt_rows) of every TT panel are only read by the discarded output rows; keep them finite
+    for (int i = threadIdx.x; i < args.tt_slots * ttslot_bytes / 16; i += kPairThreads)
+        reinterpret_cast<uint4*>(smem_tt)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t acc1_col = 0, acc2_col = 2 * C;
+
+    if (warp == 0) {
+        // ---------------- TMA producer ----------------
+        if (elect_one()) {
+            const uint32_t wbytes = n_btiles * btile_bytes;
+            mbar_expect_tx(w_full, wbytes * (args.w2_resident ? 2 : 1));
+            for (int i = 0; i < n_btiles; ++i)
+                bulk_load_1d(smem_w1 + i * btile_bytes, reinterpret_cast<const uint8_t*>(args.w1) + static_cast<size_t>(i) * btile_bytes,
+                             btile_bytes, w_full);
+            if (args.w2_resident)
+                for (int i = 0; i < n_btiles; ++i)
+                    bulk_load_1d(smem_w2 + i * btile_bytes, reinterpret_cast<const uint8_t*>(args.w2) + static_cast<size_t>(i) * btile_bytes,
+                                 btile_bytes, w_full);
+            int sx = 0, sb = 0;
+            uint32_t px = 1, pb = 1;   // parity to wait on the EMPTY barriers (first lap passes)
+            int n_issued = 0;
+            auto issue_x = [&](int idx) {
+                const int b = idx / args.tiles_t;
+                const int t0 = (idx - b * args.tiles_t) * args.m_out;
+                mbar_wait(&x_empty[sx], px, args.err_flag, 301);
+                mbar_expect_tx(&x_full[sx], xslot_bytes);
+                for (int c = 0; c < args.n_chunks; ++c)
+                    tma_load_3d(smem_x + sx * xslot_bytes + c * panel_bytes, &tmap_x, &x_full[sx], c * args.chunk_k,
+                                t0 - args.h2 - h1, b);
+                tlp_mark(args, n_issued++, 0);
+                if (++sx == args.x_slots) { sx = 0; px ^= 1; }
+            };
+            // x panels run `ahead` items in front of the W2 ring: conv2(i) is issued after conv1(i+1), so
+            // x(i+1) must never queue behind W2(i) tiles that wait for conv2(i) to drain the ring
+            const int ahead = args.x_slots - 1;
+            int nxt = blockIdx.x;
+            for (int i = 0; i < ahead && nxt < args.n_work; ++i, nxt += grid) issue_x(nxt);
+            for (int idx = blockIdx.x; idx < args.n_work; idx += grid) {
+                if (nxt < args.n_work) { issue_x(nxt); nxt += grid; }
+                if (!args.w2_resident) {
+                    const uint8_t* wp = reinterpret_cast<const uint8_t*>(args.w2);
+                    for (int i = 0; i < n_btiles; ++i) {
+                        mbar_wait(&empty_b[sb], pb, args.err_flag, 302);
+                        mbar_expect_tx(&full_b[sb], btile_bytes);
+                        bulk_load_1d(smem_w2 + sb * btile_bytes, wp, btile_bytes, &full_b[sb]);
+                        wp += btile_bytes;
+                        if (++sb == args.b_stages) { sb = 0; pb ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer (one elected thread, see conv_tc2.cu on elect.sync) ----------------
+        if (elect_one()) {
+            const uint32_t idesc = umma_idesc_f16(kTileM, C);
+            const int ksteps = args.chunk_k >> 4;
+            const uint32_t row_u = row_bytes >> 4;
+            const uint32_t desc_hi = ((8u * row_bytes) >> 4) | (1u << 14) | ((row_bytes == 128 ? 2u : 4u) << 29);
+            const uint32_t lo_flag = 1u << 16;
+            const uint32_t x_lo0 = (smem_u32(smem_x) & 0x3FFFFu) >> 4;
+            const uint32_t tt_lo0 = (smem_u32(smem_tt) & 0x3FFFFu) >> 4;
+            const uint32_t w1_lo0 = (smem_u32(smem_w1) & 0x3FFFFu) >> 4;
+            const uint32_t w2_lo0 = (smem_u32(smem_w2) & 0x3FFFFu) >> 4;
+            const uint32_t panel_u = panel_bytes >> 4, xslot_u = xslot_bytes >> 4;
+            const uint32_t ttp_u = ttp_bytes >> 4, ttslot_u = ttslot_bytes >> 4;
+            const uint32_t btile_u = btile_bytes >> 4;
+            const uint32_t tap1_u = args.dil * row_u;
+
+            int sx = 0, st = 0, sb = 0, b1 = 0, b2 = 0;
+            uint32_t pxl = 0, ptt = 0, pb = 0;          // parities of the FULL barriers
+            uint32_t pe1 = 3, pe2 = 3;                  // per-buffer parity bits of the accumulator EMPTY barriers
+
+            mbar_wait(w_full, 0, args.err_flag, 303);
+            tc_fence_after();
+
+            auto issue = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t accumulate) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (k < ksteps) {
+                        const uint64_t ad = (static_cast<uint64_t>(desc_hi) << 32) | ((a_lo + 2 * k) & 0x3FFFu) | lo_flag;
+                        const uint64_t bd = (static_cast<uint64_t>(desc_hi) << 32) | ((b_lo + 2 * k) & 0x3FFFu) | lo_flag;
+                        umma_f16(d_tmem, ad, bd, idesc, accumulate | static_cast<uint32_t>(k));
+                    }
+                }
+            };
+            int it1 = 0, it2 = 0;
+            auto conv1 = [&] {
+                mbar_wait(&xl_full[sx], pxl, args.err_flag, 304);
+                mbar_wait(&acc1_empty[b1], (pe1 >> b1) & 1u, args.err_flag, 305);
+                pe1 ^= 1u << b1;
+                tc_fence_after();
+                tlp_mark(args, it1, 3);
+                const uint32_t d = tmem_base + acc1_col + b1 * C;
+                uint32_t accumulate = 0;
+                for (int c = 0; c < args.n_chunks; ++c) {
+                    uint32_t a_lo = x_lo0 + sx * xslot_u + c * panel_u;
+                    const uint32_t b_lo = w1_lo0 + c * args.n_taps * btile_u;
+                    for (int tap = 0; tap < args.n_taps; ++tap) {
+                        issue(d, a_lo, b_lo + tap * btile_u, accumulate);
+                        accumulate = 1;
+                        a_lo += tap1_u;
+                    }
+                }
+                umma_commit(&x_empty[sx]);
+                umma_commit(&acc1_full[b1]);
+                tlp_mark(args, it1++, 4);
+                if (++sx == args.x_slots) { sx = 0; pxl ^= 1; }
+                b1 ^= 1;
+            };
+            auto conv2 = [&] {
+                mbar_wait(&tt_full[st], (ptt >> st) & 1u, args.err_flag, 306);
+                mbar_wait(&acc2_empty[b2], (pe2 >> b2) & 1u, args.err_flag, 307);
+                pe2 ^= 1u << b2;
+                tc_fence_after();
+                tlp_mark(args, it2, 5);
+                const uint32_t d = tmem_base + acc2_col + b2 * C;
+                uint32_t accumulate = 0;
+                for (int c = 0; c < args.n_chunks; ++c) {
+                    uint32_t a_lo = tt_lo0 + st * ttslot_u + c * ttp_u;
+                    for (int tap = 0; tap < args.n_taps; ++tap) {
+                        uint32_t b_lo;
+                        if (args.w2_resident) {
+                            b_lo = w2_lo0 + (c * args.n_taps + tap) * btile_u;
+                        } else {
+                            mbar_wait(&full_b[sb], pb, args.err_flag, 308);
+                            tc_fence_after();
+                            b_lo = w2_lo0 + sb * btile_u;
+                        }
+                        issue(d, a_lo, b_lo, accumulate);
+                        accumulate = 1;
+                        a_lo += row_u;
+                        if (!args.w2_resident) {
+                            umma_commit(&empty_b[sb]);
+                            if (++sb == args.b_stages) { sb = 0; pb ^= 1; }
+                        }
+                    }
+                }
+                umma_commit(&tt_empty[st]);
+                umma_commit(&acc2_full[b2]);
+                tlp_mark(args, it2++, 6);
+                ptt ^= 1u << st;
+                if (args.tt_slots == 2) st ^= 1;
+                b2 ^= 1;
+            };
+            bool first = true;
+            for (int idx = blockIdx.x; idx < args.n_work; idx += grid) {
+                conv1();
+                if (!first) conv2();
+                first = false;
+            }
+            if (!first) conv2();
+        }
+    } else if (warp < 4) {
+        // ---------------- lrelu transform, in place on the landed x panel ----------------
+        const int tid = threadIdx.x - 64;
+        const __half2 slope2 = __float2half2_rn(args.slope);
+        const int units = xslot_bytes >> 4;
+        int sx = 0, it = 0;
+        uint32_t px = 0;
+        for (int idx = blockIdx.x; idx < args.n_work; idx += grid, ++it) {
+            mbar_wait(&x_full[sx], px, args.err_flag, 309);
+            if (tid == 0) tlp_mark(args, it, 1);
+            const uint32_t base = smem_u32(smem_x + sx * xslot_bytes);
+            for (int i = tid; i < units; i += 64) {
+                uint4 v = lds128(base + i * 16);
+                v.x = lrelu_h2(v.x, slope2); v.y = lrelu_h2(v.y, slope2);
+                v.z = lrelu_h2(v.z, slope2); v.w = lrelu_h2(v.w, slope2);
+                sts128(base + i * 16, v);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (elect_one()) mbar_arrive(&xl_full[sx]);
+            if (tid == 0) tlp_mark(args, it, 2);
+            if (++sx == args.x_slots) { sx = 0; px ^= 1; }
+        }
+    } else if (warp < 8) {
+        // ---------------- mid epilogue: acc1 -> lrelu(acc + b1) * rowmask -> TT panel (UMMA layout) ----------------
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        int b1 = 0, st = 0;
+        uint32_t pf = 0;
+        uint32_t pte = 3;   // per-slot parity bits to wait on tt_empty (first lap passes)
+        const float slope = args.slope;
+        const uint32_t phase = row_bytes == 128 ? (m & 7) : ((m >> 1) & 3);
+        int it = 0;
+        for (int idx = blockIdx.x; idx < args.n_work; idx += grid, ++it) {
+            const int b = idx / args.tiles_t;
+            const int t0 = (idx - b * args.tiles_t) * args.m_out;
+            const int t = t0 - args.h2 + m;
+            int len_rows = args.T;
+            if (args.epi.lens != nullptr) len_rows = min(len_rows, __ldg(args.epi.lens + b) * args.epi.len_mul);
+            const bool valid = t >= 0 && t < len_rows;
+            mbar_wait(&acc1_full[b1], (pf >> b1) & 1u, args.err_flag, 310);
+            pf ^= 1u << b1;
+            tc_fence_after();
+            if (m == 0) tlp_mark(args, it, 7);
+            mbar_wait(&tt_empty[st], (pte >> st) & 1u, args.err_flag, 311);
+            pte ^= 1u << st;
+            if (m == 0) tlp_mark(args, it, 8);
+            const uint32_t tt_base = smem_u32(smem_tt + st * ttslot_bytes) + m * row_bytes;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc1_col + b1 * C;
+            for (int c0 = 0; c0 < C; c0 += 32) {
+                float v[32];
+                tmem_ld32(taddr + c0, v);
+                const int chunk = c0 / args.chunk_k;
+                const int u0 = (c0 - chunk * args.chunk_k) >> 3;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    float bs[8], a[8];
+                    bias8(args.bias1, c0 + g * 8, bs);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float y = v[g * 8 + j] + bs[j];
+                        a[j] = valid ? (y > 0.f ? y : y * slope) : 0.f;
+                    }
+                    sts128(tt_base + chunk * ttp_bytes + ((u0 + g) ^ phase) * 16, pack8(a));
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            __syncwarp();
+            if (elect_one()) {
+                mbar_arrive(&acc1_empty[b1]);
+                mbar_arrive(&tt_full[st]);
+            }
+            if (m == 0) tlp_mark(args, it, 9);
+            b1 ^= 1;
+            if (args.tt_slots == 2) st ^= 1;
+        }
+    } else {
+        // ---------------- final epilogue: acc2 + b2 + x -> mask -> outputs (lean epilogue) ----------------
+        const int q = warp & 3;
+        constexpr bool kMrf = kEpi == 2;
+        uint8_t* stage = smem_stage + q * 2048;
+        int b2 = 0;
+        uint32_t pf = 0;
+        LeanPrefetch<kMrf> pre_cur, pre_nxt;
+        if (blockIdx.x < args.n_work) {
+            const int b0 = blockIdx.x / args.tiles_t;
+            const int t00 = (blockIdx.x - b0 * args.tiles_t) * args.m_out;
+            const int w0 = t00 + q * 32;
+            RowIO io{stage, lane, min(32, max(0, min(args.T, t00 + args.m_out) - w0))};
+            lean_prefetch(args.epi, io, static_cast<long>(b0) * args.T + w0, 0, true, pre_cur);
+        }
+        int it = 0;
+        const bool tl_on = q == 0 && lane == 0;
+        for (int idx = blockIdx.x; idx < args.n_work; idx += grid, ++it) {
+            const int b = idx / args.tiles_t;
+            const int t0 = (idx - b * args.tiles_t) * args.m_out;
+            const int t = t0 + q * 32 + lane;
+            if (tl_on) tlp_mark(args, it, 10);
+            TmemAcc acc{tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc2_col + b2 * C};
+            const uint32_t par = (pf >> b2) & 1u;
+            auto wait_acc = [&] {
+                mbar_wait(&acc2_full[b2], par, args.err_flag, 312);
+                tc_fence_after();
+                if (tl_on) tlp_mark(args, it, 11);
+            };
+            auto drained = [&] {
+                tc_fence_before();
+                __syncwarp();
+                if (elect_one()) mbar_arrive(&acc2_empty[b2]);
+            };
+            const int nidx = idx + grid;
+            const bool nvalid = nidx < args.n_work;
+            const int nb = nvalid ? nidx / args.tiles_t : 0;
+            const int nt0 = nvalid ? (nidx - nb * args.tiles_t) * args.m_out : 0;
+            const int nw0 = nt0 + q * 32;
+            RowIO nio{stage, lane, min(32, max(0, min(args.T, nt0 + args.m_out) - nw0))};
+            lean_prefetch(args.epi, nio, static_cast<long>(nb) * args.T + nw0, 0, nvalid, pre_nxt);
+            run_epilogue_lean<kMrf>(args.epi, acc, b, t, 0, C, wait_acc, drained, stage, pre_cur, t0 + args.m_out);
+            pre_cur = pre_nxt;
+            if (tl_on) tlp_mark(args, it, 12);
+            pf ^= 1u << b2;
+            b2 ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------------
+static const size_t kPairSmemMax = 232448;
+static const size_t kPairFixed = 1024 /*alignment*/ + 1024 /*barriers + tmem slot*/ + 8192 /*staging*/ + 256;
+
+ConvPairPlan conv_pair_plan(const ConvLayer& L1, const ConvLayer& L2) {
+    ConvPairPlan p;
+    static const int enabled = getenv("TTSB_PAIR") ? atoi(getenv("TTSB_PAIR")) : 1;
+    if (!enabled) return p;
+    const int C = L1.n_total;
+    if (L1.cin != C || L2.cin != C || L2.n_total != C || L1.n_tile != C || L2.n_tile != C) return p;
+    if (L1.n_taps != L2.n_taps || L1.n_taps % 2 != 1 || L1.chunk_k != L2.chunk_k) return p;
+    if (C % 32 != 0 || 4 * C > 512 || C % L1.chunk_k != 0) return p;
+    const int k = L1.n_taps, h2 = (k - 1) / 2;
+    const int dil = k > 1 ? L1.tap_off[0][1] - L1.tap_off[0][0] : 1;
+    for (int i = 0; i < k; ++i) {
+        if (L1.tap_off[0][i] != (i - h2) * dil || L2.tap_off[0][i] != i - h2) return p;
+        if (L1.tap_off[1][i] != L1.tap_off[0][i] || L2.tap_off[1][i] != L2.tap_off[0][i]) return p;
+    }
+    if (dil < 1 || L1.bias == nullptr || L2.bias == nullptr) return p;
+    p.C = C; p.h2 = h2; p.dil = dil;
+    p.m_out = kTileM - 2 * h2;
+    if (p.m_out < 64) return p;
+    p.rows_panel = round_up(kTileM + 2 * h2 * dil, 8);
+    p.tt_rows = round_up(kTileM + 2 * h2, 8);
+    if (p.rows_panel > 256) return p;
+    const size_t row_bytes = L1.chunk_k * 2;
+    const size_t xslot = static_cast<size_t>(L1.n_chunks) * p.rows_panel * row_bytes;
+    const size_t ttslot = static_cast<size_t>(L1.n_chunks) * p.tt_rows * row_bytes;
+    const size_t btile = static_cast<size_t>(C) * row_bytes;
+    const size_t w1 = static_cast<size_t>(L1.n_chunks) * k * btile;
+    const size_t avail = kPairSmemMax - kPairFixed;
+    static const int force_stream = getenv("TTSB_PAIR_STREAM") ? atoi(getenv("TTSB_PAIR_STREAM")) : 0;
+    for (int res = force_stream ? 0 : 1; res >= 0 && !p.ok; --res) {
+        const int min_b = std::min<int>(4, L1.n_chunks * k);
+        const size_t wbytes = w1 + (res ? w1 : min_b * btile);
+        if (wbytes + 2 * xslot + ttslot > avail) continue;
+        const size_t rem = avail - wbytes;
+        p.tt_slots = rem >= 2 * ttslot + 2 * xslot ? 2 : 1;
+        p.x_slots = static_cast<int>(std::min<size_t>(res ? 6 : 3, (rem - p.tt_slots * ttslot) / xslot));
+        p.w2_resident = res;
+        p.b_stages = 1;
+        if (!res) {
+            const size_t left = rem - p.tt_slots * ttslot - p.x_slots * xslot;
+            p.b_stages = static_cast<int>(std::min<size_t>(kPairMaxB, min_b + left / btile));
+            p.b_stages = std::min(p.b_stages, L1.n_chunks * k);
+        }
+        p.smem_bytes = kPairFixed + p.x_slots * xslot + p.tt_slots * ttslot + w1 + (res ? w1 : p.b_stages * btile);
+        p.ok = 1;
+    }
+    p.tmem_cols = 32;
+    while (p.tmem_cols < 4 * C) p.tmem_cols *= 2;
+    return p;
+}
+
+template <int kCols, int kEpi>
+static int launch_pair(const CUtensorMap& tm, const ConvPairArgs& a, int grid, size_t smem, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        TTSB_CHECK_CUDA(cudaFuncSetAttribute(conv_pair_kernel<kCols, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(kPairSmemMax)));
+        configured = true;
+    }
+    conv_pair_kernel<kCols, kEpi><<<grid, kPairThreads, smem, s>>>(tm, a);
+    count_launch();
+    TTSB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int conv_pair_forward(const ConvLayer& L1, const ConvLayer& L2, const ConvPairPlan& plan, const ConvRuntime& rt,
+                      const __half* x, int B, int T, float slope, EpiParams epi, cudaStream_t stream) {
+    TTSB_REQUIRE(plan.ok, "conv pair plan is not feasible");
+    TTSB_REQUIRE(B > 0 && T > 0, "empty batch");
+    TTSB_REQUIRE(slope > 0.f && slope < 1.f, "leaky-relu slope must be in (0, 1)");
+    TTSB_REQUIRE(epi.ln_g == nullptr && epi.head_w == nullptr && epi.out_f32 == nullptr && epi.out_f32_t == nullptr &&
+                     epi.act_tanh == 0 && epi.pre_ln_relu == 0,
+                 "conv pair supports the lean epilogue only");
+    const CUtensorMap* tm = nullptr;
+    TTSB_PROPAGATE(get_act_tensor_map(x, plan.C, B, T, plan.C, L1.chunk_k, plan.rows_panel, &tm));
+    ConvPairArgs a;
+    a.B = B; a.T = T;
+    a.m_out = plan.m_out;
+    a.tiles_t = ceil_div(T, plan.m_out);
+    a.n_work = B * a.tiles_t;
+    a.C = plan.C; a.chunk_k = L1.chunk_k; a.n_chunks = L1.n_chunks; a.n_taps = L1.n_taps;
+    a.h2 = plan.h2; a.dil = plan.dil;
+    a.rows_panel = plan.rows_panel; a.tt_rows = plan.tt_rows;
+    a.x_slots = plan.x_slots; a.tt_slots = plan.tt_slots;
+    a.w2_resident = plan.w2_resident; a.b_stages = plan.b_stages;
+    a.w1 = L1.w_packed; a.w2 = L2.w_packed;
+    a.bias1 = L1.bias;
+    a.slope = slope;
+    a.err_flag = rt.err_flag;
+    a.timeline = rt.timeline;
+    epi.T = T;
+    epi.n_total = plan.C;
+    epi.bias = L2.bias;
+    epi.residual = x;
+    epi.ld_res = plan.C;
+    a.epi = epi;
+    const int grid = std::min(num_sms(), a.n_work);
+    const bool mrf = epi.mrf_mode != MRF_NONE;
+    switch (plan.tmem_cols) {
+        case 128: return mrf ? launch_pair<128, 2>(*tm, a, grid, plan.smem_bytes, stream)
+                             : launch_pair<128, 1>(*tm, a, grid, plan.smem_bytes, stream);
+        case 256: return mrf ? launch_pair<256, 2>(*tm, a, grid, plan.smem_bytes, stream)
+                             : launch_pair<256, 1>(*tm, a, grid, plan.smem_bytes, stream);
+        case 512: return mrf ? launch_pair<512, 2>(*tm, a, grid, plan.smem_bytes, stream)
+                             : launch_pair<512, 1>(*tm, a, grid, plan.smem_bytes, stream);
+    }
+    TTSB_REQUIRE(false, "bad tmem_cols for conv pair");
+    return 1;
+}
+
+}  // namespace ttsb

@@ -347,7 +347,42 @@ static PFN_encodeTiled2 get_encode_fn2() {
     return fn;
 }
 
-static int num_sms() {
+// 3-D tensor map over channel-last activations [B][T][cin] (row pitch ld_in) with a box of
+// chunk_k channels x rows_panel rows; out-of-range rows are zero-filled (= conv zero padding).
+// Tensor maps are pure functions of (pointer, geometry): memoise them, the same workspace buffers
+// come back every step (host time matters once a step is ~10^3 launches of ~50 us).
+int get_act_tensor_map(const __half* in, int ld_in, int B, int T, int cin, int chunk_k, int rows_panel,
+                       const CUtensorMap** out) {
+    PFN_encodeTiled2 enc = get_encode_fn2();
+    TTSB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled driver entry point not available");
+    TTSB_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (ld_in % 8) == 0, "input alignment");
+    struct TmKey {
+        const void* p; int ld, B, T, cin, ck, rows;
+        bool operator==(const TmKey& o) const {
+            return p == o.p && ld == o.ld && B == o.B && T == o.T && cin == o.cin && ck == o.ck && rows == o.rows;
+        }
+    };
+    static thread_local std::vector<std::pair<TmKey, CUtensorMap>> cache;
+    const TmKey key{in, ld_in, B, T, cin, chunk_k, rows_panel};
+    for (auto& kv : cache)
+        if (kv.first == key) { *out = &kv.second; return 0; }
+    CUtensorMap tm_new;
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(cin), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(B)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld_in) * 2, static_cast<cuuint64_t>(T) * ld_in * 2};
+    cuuint32_t box[3] = {static_cast<cuuint32_t>(chunk_k), static_cast<cuuint32_t>(rows_panel), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&tm_new, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(in), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     chunk_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TTSB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r)));
+    if (cache.size() >= 256) cache.clear();   // pointers handed out earlier are not kept across calls
+    cache.emplace_back(key, tm_new);
+    *out = &cache.back().second;
+    return 0;
+}
+
+int num_sms() {
     static int n = 0;
     if (!n) {
         int dev = 0;
@@ -401,9 +436,6 @@ static int launch_two(const CUtensorMap& tm, const ConvTc2Args& a, int grid, siz
 
 int conv_forward_tc2(const ConvLayer& L, const ConvRuntime& rt, const __half* in, int ld_in, int B,
                      int T, const EpiParams& epi, cudaStream_t stream) {
-    PFN_encodeTiled2 enc = get_encode_fn2();
-    TTSB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled driver entry point not available");
-    TTSB_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (ld_in % 8) == 0, "input alignment");
     TTSB_REQUIRE(ld_in >= L.cin, "input row pitch smaller than layer Cin");
     // tap offsets must be an arithmetic sequence per class (true for conv, transposed conv, linear)
     int step[2] = {0, 0};
@@ -413,34 +445,8 @@ int conv_forward_tc2(const ConvLayer& L, const ConvRuntime& rt, const __half* in
             TTSB_REQUIRE(L.tap_off[c][i] - L.tap_off[c][i - 1] == step[c], "tap offsets must be equally spaced");
     }
 
-    // tensor maps are pure functions of (pointer, geometry): memoise them, the same workspace buffers
-    // come back every step (host time matters once a step is ~10^3 launches of ~50 us)
-    struct TmKey {
-        const void* p; int ld, B, T, cin, ck, rows;
-        bool operator==(const TmKey& o) const {
-            return p == o.p && ld == o.ld && B == o.B && T == o.T && cin == o.cin && ck == o.ck && rows == o.rows;
-        }
-    };
-    static thread_local std::vector<std::pair<TmKey, CUtensorMap>> cache;
-    const TmKey key{in, ld_in, B, T, L.cin, L.chunk_k, L.rows_panel};
     const CUtensorMap* tmp = nullptr;
-    for (auto& kv : cache)
-        if (kv.first == key) { tmp = &kv.second; break; }
-    if (tmp == nullptr) {
-        CUtensorMap tm_new;
-        cuuint64_t dims[3] = {static_cast<cuuint64_t>(L.cin), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(B)};
-        cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld_in) * 2, static_cast<cuuint64_t>(T) * ld_in * 2};
-        cuuint32_t box[3] = {static_cast<cuuint32_t>(L.chunk_k), static_cast<cuuint32_t>(L.rows_panel), 1};
-        cuuint32_t estr[3] = {1, 1, 1};
-        CUresult r = enc(&tm_new, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(in), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         L.chunk_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        TTSB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r)));
-        if (cache.size() >= 256) cache.clear();
-        cache.emplace_back(key, tm_new);
-        tmp = &cache.back().second;
-    }
+    TTSB_PROPAGATE(get_act_tensor_map(in, ld_in, B, T, L.cin, L.chunk_k, L.rows_panel, &tmp));
     const CUtensorMap& tm = *tmp;
 
     ConvTc2Args a;

@@ -361,12 +361,13 @@ __device__ __forceinline__ void lean_prefetch(const EpiParams& e, const RowIO& i
 template <bool kMrf, class Acc, class WaitFn, class DrainFn>
 __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc& acc, int b, int t, int n_base,
                                                   int n_tile, WaitFn wait_acc, DrainFn acc_drained, uint8_t* stage,
-                                                  const LeanPrefetch<kMrf>& pre) {
+                                                  const LeanPrefetch<kMrf>& pre, int t_end = 0x7fffffff) {
+    // t_end: exclusive row limit of this tile's stores (conv_pair tiles own fewer than 128 rows)
     const int lane = threadIdx.x & 31;
     const int warp_row0 = t - lane;
     const long row0 = static_cast<long>(b) * e.T + warp_row0;
     const bool in_len = e.lens == nullptr || t < __ldg(e.lens + b) * e.len_mul;
-    RowIO io{stage, lane, min(32, max(0, e.T - warp_row0))};
+    RowIO io{stage, lane, min(32, max(0, min(e.T, t_end) - warp_row0))};
     const bool use_res = e.residual != nullptr;
     const bool use_mrf = kMrf && (e.mrf_mode == MRF_ADD || e.mrf_mode == MRF_LAST);
     const bool mrf_store = kMrf && (e.mrf_mode == MRF_FIRST || e.mrf_mode == MRF_ADD);

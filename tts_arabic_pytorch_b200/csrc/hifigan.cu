@@ -10,6 +10,8 @@
 //     conv2  : in  = TT, residual = p==0 ? X0 : XA
 //              p<2 : XA = v, LXA = lrelu(v)
 //              p==2: MRF accumulate v/3 into XS; on the last resblock emit NXT = lrelu(XS_total)
+// Pairs with a feasible ConvPairPlan (C <= 64) run conv1+conv2 as ONE launch (conv_pair.cu): raw tensors only,
+//     pair   : in = p==0 ? X0 : (p==1 ? XA : XB), out = p==0 ? XA : XB  (p==2: MRF accumulate as above)
 // Every epilogue zeroes rows beyond the utterance's own length so that a padded batch sees the
 // same zero padding as the reference's per-utterance calls (models/fastpitch/networks.py:340-345).
 #include <cstdlib>
@@ -25,6 +27,7 @@ struct ttsb_hifigan {
     ConvLayer conv_pre;
     std::vector<ConvLayer> ups;
     std::vector<ConvLayer> c1, c2;  // index ((stage*num_kernels)+j)*3+p
+    std::vector<ConvPairPlan> pair; // same index: fused (c1, c2) launch plan, ok = 0 -> two launches
     float* post_w = nullptr;        // [7][32] tap-major
     float post_b = 0.f;
     int post_k = 7;
@@ -148,6 +151,7 @@ int ttsb_hifigan_create(const ttsb_hifigan_config_t* cfg, const ttsb_tensor_t* w
     h->ups.resize(cfg->num_upsamples);
     h->c1.resize(cfg->num_upsamples * cfg->num_kernels * 3);
     h->c2.resize(cfg->num_upsamples * cfg->num_kernels * 3);
+    h->pair.resize(cfg->num_upsamples * cfg->num_kernels * 3);
     for (int i = 0; i < cfg->num_upsamples; ++i) {
         const int cout = cin / 2, s = cfg->upsample_rates[i], k = cfg->upsample_kernel_sizes[i];
         const std::string pre = "ups." + std::to_string(i);
@@ -170,6 +174,7 @@ int ttsb_hifigan_create(const ttsb_hifigan_config_t* cfg, const ttsb_tensor_t* w
                 TTSB_PROPAGATE(make_conv1d_layer(h->c1[idx], w1->h_data, b1->h_data, cout, cout, rk,
                                                  cfg->resblock_dilations[j][p], cout, 0));
                 TTSB_PROPAGATE(make_conv1d_layer(h->c2[idx], w2->h_data, b2->h_data, cout, cout, rk, 1, cout, 0));
+                h->pair[idx] = conv_pair_plan(h->c1[idx], h->c2[idx]);
             }
         }
         cin = cout;
@@ -235,6 +240,8 @@ int ttsb_hifigan_forward(ttsb_hifigan_t* h, const float* d_mel_f32, const void* 
     for (int i = 0; i < 8; ++i) buf[i] = c.take<__half>(static_cast<size_t>(bc_max) * T * h->max_elems_per_frame);
     __half *NXT[2] = {buf[0], buf[1]}, *X0 = buf[2], *LX0 = buf[3], *TT = buf[4], *XA = buf[5], *LXA = buf[6],
            *XS = buf[7];
+    __half* XB = TT;   // a resblock is either fused (X0 -> XA -> XB) or not (LX0/TT/XA/LXA); they run one after another
+    const bool use_pair = rt.impl == IMPL_TC && rt.tc_version == 2;
 
     for (int b0 = 0; b0 < B; b0 += bc_max) {
         const int bc = std::min(bc_max, B - b0);
@@ -258,11 +265,14 @@ int ttsb_hifigan_forward(ttsb_hifigan_t* h, const float* d_mel_f32, const void* 
         int up = 1;
         for (int i = 0; i < cfg.num_upsamples; ++i) {
             const int s = cfg.upsample_rates[i], C = cin / 2;
+            bool any_unfused = false;
+            for (int j = 0; j < cfg.num_kernels * 3; ++j) any_unfused |= !(use_pair && h->pair[i * cfg.num_kernels * 3 + j].ok);
             {
                 EpiParams e;
                 e.lens = lens; e.len_mul = up;
                 e.out_raw = X0; e.ld_raw = s * C;
-                e.out_act = LX0; e.ld_act = s * C; e.act_slope = 0.1f;
+                if (any_unfused) { e.out_act = LX0; e.ld_act = s * C; }
+                e.act_slope = 0.1f;
                 TTSB_PROPAGATE(conv_forward(h->ups[i], rt, NXT[cur], cin, bc, T * up, e, stream));
             }
             up *= s;
@@ -271,7 +281,9 @@ int ttsb_hifigan_forward(ttsb_hifigan_t* h, const float* d_mel_f32, const void* 
             for (int j = 0; j < cfg.num_kernels; ++j) {
                 for (int p = 0; p < 3; ++p) {
                     const int idx = (i * cfg.num_kernels + j) * 3 + p;
-                    {
+                    // a resblock is fused as a whole or not at all (its three pairs share k and C)
+                    const bool fused = use_pair && h->pair[idx - p].ok && h->pair[idx - p + 1].ok && h->pair[idx - p + 2].ok;
+                    if (!fused) {
                         EpiParams e;
                         e.lens = lens; e.len_mul = up;
                         e.out_act = TT; e.ld_act = C; e.act_slope = 0.1f;
@@ -281,8 +293,9 @@ int ttsb_hifigan_forward(ttsb_hifigan_t* h, const float* d_mel_f32, const void* 
                     e.lens = lens; e.len_mul = up;
                     e.residual = p == 0 ? X0 : XA; e.ld_res = C;
                     if (p < 2) {
-                        e.out_raw = XA; e.ld_raw = C;
-                        e.out_act = LXA; e.ld_act = C; e.act_slope = 0.1f;
+                        e.out_raw = fused && p == 1 ? XB : XA; e.ld_raw = C;
+                        if (!fused) { e.out_act = LXA; e.ld_act = C; }
+                        e.act_slope = 0.1f;
                     } else {
                         e.mrf_buf = XS;
                         e.mrf_scale = 1.f / static_cast<float>(cfg.num_kernels);
@@ -298,7 +311,12 @@ int ttsb_hifigan_forward(ttsb_hifigan_t* h, const float* d_mel_f32, const void* 
                             e.act_slope = last_stage ? 0.01f : 0.1f;
                         }
                     }
-                    TTSB_PROPAGATE(conv_forward(h->c2[idx], rt, TT, C, bc, rows, e, stream));
+                    if (fused) {
+                        const __half* xin = p == 0 ? X0 : (p == 1 ? XA : XB);
+                        TTSB_PROPAGATE(conv_pair_forward(h->c1[idx], h->c2[idx], h->pair[idx], rt, xin, bc, rows, 0.1f, e, stream));
+                    } else {
+                        TTSB_PROPAGATE(conv_forward(h->c2[idx], rt, TT, C, bc, rows, e, stream));
+                    }
                 }
             }
             cur ^= 1;
