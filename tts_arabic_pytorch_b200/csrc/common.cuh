@@ -111,12 +111,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 
-// Bounded wait: a protocol bug must surface as an error code in `*err_flag`, never as a hung
-// GPU box. ~2^31 polls of a HW-sleeping try_wait is many seconds; normal waits take microseconds.
+// try_wait with a suspend-time hint (ns): the warp sleeps in hardware until the phase completes or the hint
+// expires, instead of coming back every few hundred cycles to re-issue the poll.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+        : "memory");
+    return ok != 0;
+}
+
+// Bounded wait: a protocol bug must surface as an error code in `*err_flag`, never as a hung GPU box
+// (a few seconds of SM clocks; normal waits take microseconds).
+// The poll loop matters: with the default (short) try_wait time limit every waiting warp re-issues its
+// poll + loop bookkeeping every few hundred cycles, and with ~10 warps of a CTA waiting at any time those
+// instructions took ~1/3 of the SM's issue slots away from the MMA-issuing thread and the epilogue warps
+// (profiles/r01_s24_ncu_full_b64.csv: issue-active 48 %, ALU pipe 39 % in a kernel that is mostly waiting).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag, int code) {
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_hint(bar, parity, 100000u)) {
+        if (clock64() - t0 > 6000000000ll) {
             if (err_flag) atomicExch(err_flag, code);
             __trap();
         }

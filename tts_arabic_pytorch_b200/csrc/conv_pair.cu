@@ -19,14 +19,15 @@
 // MMA issue order is conv1(i+1) before conv2(i), so the tensor pipe works on the next tile while the
 // mid epilogue turns acc1(i) into TT(i); both accumulators are double-buffered in TMEM (4*C columns).
 //
-// Warp roles (384 threads): 0 TMA producer, 1 MMA issuer, 2-3 lrelu transform, 4-7 mid epilogue,
-// 8-11 final epilogue (the lean epilogue of epilogue.cuh).
+// Warp roles (512 threads): 0 TMA producer (x panels, resident weights), 1 conv1 MMA issuer, 2 conv2 MMA issuer,
+// 3 W2 ring producer (streamed W2 only), 4-7 mid epilogue, 8-11 final epilogue (the lean epilogue of
+// epilogue.cuh), 12-15 lrelu transform.
 #include <cstdlib>
 #include "conv.cuh"
 
 namespace ttsb {
 
-constexpr int kPairThreads = 384;
+constexpr int kPairThreads = 512;
 constexpr int kPairMaxX = 8;
 constexpr int kPairMaxB = 8;
 
@@ -47,6 +48,8 @@ struct ConvPairArgs {
     const float* bias1;
     float slope;
     int* err_flag;
+    int debug;        // timing-decomposition switches (TTSB_PAIR_DEBUG; results are wrong when set): 1 no lrelu transform,
+                      // 2 no TT stores, 4 no final epilogue work, 8 no MMAs
     long long* timeline;   // debug (tools/timeline_pair.py): 128 clock64() slots per CTA for the first 256 CTAs, or null
     EpiParams epi;    // final epilogue: bias = b2, residual = x, outputs
 };
@@ -65,9 +68,11 @@ __device__ __forceinline__ uint32_t lrelu_h2(uint32_t u, __half2 slope2) {
     return *reinterpret_cast<uint32_t*>(&y);
 }
 
+// kTmemCols = 4 * C: 128 -> C = 32 (32-channel rows, 64 B swizzle, 2 K steps per tap), 256 / 512 -> C = 64 / 128
 template <int kTmemCols, int kEpi>
 __global__ void __launch_bounds__(kPairThreads, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ ConvPairArgs args) {
+    constexpr int kKSteps = kTmemCols == 128 ? 2 : 4;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_u32 = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw_u32 & 1023u)) & 1023u);
@@ -109,7 +114,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     if (warp == 0 && elect_one()) {
         if (args.timeline != nullptr && blockIdx.x < 256) args.timeline[blockIdx.x * 128] = clock64();
         tma_prefetch_desc(&tmap_x);
-        for (int i = 0; i < args.x_slots; ++i) { mbar_init(&x_full[i], 1); mbar_init(&xl_full[i], 2); mbar_init(&x_empty[i], 1); }
+        for (int i = 0; i < args.x_slots; ++i) { mbar_init(&x_full[i], 1); mbar_init(&xl_full[i], 4); mbar_init(&x_empty[i], 1); }
         for (int i = 0; i < args.b_stages; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tt_full[i], 4); mbar_init(&tt_empty[i], 1);
@@ -131,7 +136,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     const uint32_t acc1_col = 0, acc2_col = 2 * C;
 
     if (warp == 0) {
-        // ---------------- TMA producer ----------------
+        // ---------------- TMA producer: resident weights once, then one x panel per item ----------------
         if (elect_one()) {
             const uint32_t wbytes = n_btiles * btile_bytes;
             mbar_expect_tx(w_full, wbytes * (args.w2_resident ? 2 : 1));
@@ -142,10 +147,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 for (int i = 0; i < n_btiles; ++i)
                     bulk_load_1d(smem_w2 + i * btile_bytes, reinterpret_cast<const uint8_t*>(args.w2) + static_cast<size_t>(i) * btile_bytes,
                                  btile_bytes, w_full);
-            int sx = 0, sb = 0;
-            uint32_t px = 1, pb = 1;   // parity to wait on the EMPTY barriers (first lap passes)
-            int n_issued = 0;
-            auto issue_x = [&](int idx) {
+            int sx = 0, it = 0;
+            uint32_t px = 1;   // parity to wait on the EMPTY barrier (first lap passes)
+            for (int idx = blockIdx.x; idx < args.n_work; idx += grid, ++it) {
                 const int b = idx / args.tiles_t;
                 const int t0 = (idx - b * args.tiles_t) * args.m_out;
                 mbar_wait(&x_empty[sx], px, args.err_flag, 301);
@@ -153,132 +157,124 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 for (int c = 0; c < args.n_chunks; ++c)
                     tma_load_3d(smem_x + sx * xslot_bytes + c * panel_bytes, &tmap_x, &x_full[sx], c * args.chunk_k,
                                 t0 - args.h2 - h1, b);
-                tlp_mark(args, n_issued++, 0);
+                tlp_mark(args, it, 0);
                 if (++sx == args.x_slots) { sx = 0; px ^= 1; }
-            };
-            // x panels run `ahead` items in front of the W2 ring: conv2(i) is issued after conv1(i+1), so
-            // x(i+1) must never queue behind W2(i) tiles that wait for conv2(i) to drain the ring
-            const int ahead = args.x_slots - 1;
-            int nxt = blockIdx.x;
-            for (int i = 0; i < ahead && nxt < args.n_work; ++i, nxt += grid) issue_x(nxt);
+            }
+        }
+    } else if (warp == 3) {
+        // ---------------- W2 ring producer (only when W2 does not fit next to W1) ----------------
+        // its own warp: an x load must never queue behind W2 tiles that wait for conv2 to drain the ring
+        if (!args.w2_resident && elect_one()) {
+            int sb = 0;
+            uint32_t pb = 1;
             for (int idx = blockIdx.x; idx < args.n_work; idx += grid) {
-                if (nxt < args.n_work) { issue_x(nxt); nxt += grid; }
-                if (!args.w2_resident) {
-                    const uint8_t* wp = reinterpret_cast<const uint8_t*>(args.w2);
-                    for (int i = 0; i < n_btiles; ++i) {
-                        mbar_wait(&empty_b[sb], pb, args.err_flag, 302);
-                        mbar_expect_tx(&full_b[sb], btile_bytes);
-                        bulk_load_1d(smem_w2 + sb * btile_bytes, wp, btile_bytes, &full_b[sb]);
-                        wp += btile_bytes;
-                        if (++sb == args.b_stages) { sb = 0; pb ^= 1; }
-                    }
+                const uint8_t* wp = reinterpret_cast<const uint8_t*>(args.w2);
+                for (int i = 0; i < n_btiles; ++i) {
+                    mbar_wait(&empty_b[sb], pb, args.err_flag, 302);
+                    mbar_expect_tx(&full_b[sb], btile_bytes);
+                    bulk_load_1d(smem_w2 + sb * btile_bytes, wp, btile_bytes, &full_b[sb]);
+                    wp += btile_bytes;
+                    if (++sb == args.b_stages) { sb = 0; pb ^= 1; }
                 }
             }
         }
-    } else if (warp == 1) {
-        // ---------------- MMA issuer (one elected thread, see conv_tc2.cu on elect.sync) ----------------
+    } else if (warp == 1 || warp == 2) {
+        // ---------------- MMA issuers: warp 1 issues every conv1, warp 2 every conv2 ----------------
+        // Two threads because the per-item serial chain of ONE issuer (4 barrier waits, 2 x k MMAs, 4 commits)
+        // was the tile period (profiles/r01_s25_pair_decomposition.txt); the tensor pipe interleaves both streams.
+        // One elected thread each (see conv_tc2.cu on elect.sync).
         if (elect_one()) {
             const uint32_t idesc = umma_idesc_f16(kTileM, C);
-            const int ksteps = args.chunk_k >> 4;
             const uint32_t row_u = row_bytes >> 4;
-            const uint32_t desc_hi = ((8u * row_bytes) >> 4) | (1u << 14) | ((row_bytes == 128 ? 2u : 4u) << 29);
-            const uint32_t lo_flag = 1u << 16;
-            const uint32_t x_lo0 = (smem_u32(smem_x) & 0x3FFFFu) >> 4;
-            const uint32_t tt_lo0 = (smem_u32(smem_tt) & 0x3FFFFu) >> 4;
-            const uint32_t w1_lo0 = (smem_u32(smem_w1) & 0x3FFFFu) >> 4;
-            const uint32_t w2_lo0 = (smem_u32(smem_w2) & 0x3FFFFu) >> 4;
-            const uint32_t panel_u = panel_bytes >> 4, xslot_u = xslot_bytes >> 4;
-            const uint32_t ttp_u = ttp_bytes >> 4, ttslot_u = ttslot_bytes >> 4;
+            const uint64_t desc_hi = (static_cast<uint64_t>(((8u * row_bytes) >> 4) | (1u << 14) | ((row_bytes == 128 ? 2u : 4u) << 29)) << 32) |
+                                     (1u << 16);
             const uint32_t btile_u = btile_bytes >> 4;
-            const uint32_t tap1_u = args.dil * row_u;
-
-            int sx = 0, st = 0, sb = 0, b1 = 0, b2 = 0;
-            uint32_t pxl = 0, ptt = 0, pb = 0;          // parities of the FULL barriers
-            uint32_t pe1 = 3, pe2 = 3;                  // per-buffer parity bits of the accumulator EMPTY barriers
-
+            auto issue = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t accumulate) {
+                if (args.debug & 8) return;
+#pragma unroll
+                for (int k = 0; k < kKSteps; ++k)
+                    umma_f16(d_tmem, desc_hi | ((a_lo + 2 * k) & 0x3FFFu), desc_hi | ((b_lo + 2 * k) & 0x3FFFu), idesc,
+                             accumulate | static_cast<uint32_t>(k));
+            };
             mbar_wait(w_full, 0, args.err_flag, 303);
             tc_fence_after();
-
-            auto issue = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t accumulate) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (k < ksteps) {
-                        const uint64_t ad = (static_cast<uint64_t>(desc_hi) << 32) | ((a_lo + 2 * k) & 0x3FFFu) | lo_flag;
-                        const uint64_t bd = (static_cast<uint64_t>(desc_hi) << 32) | ((b_lo + 2 * k) & 0x3FFFu) | lo_flag;
-                        umma_f16(d_tmem, ad, bd, idesc, accumulate | static_cast<uint32_t>(k));
-                    }
-                }
-            };
-            int it1 = 0, it2 = 0;
-            auto conv1 = [&] {
-                mbar_wait(&xl_full[sx], pxl, args.err_flag, 304);
-                mbar_wait(&acc1_empty[b1], (pe1 >> b1) & 1u, args.err_flag, 305);
-                pe1 ^= 1u << b1;
-                tc_fence_after();
-                tlp_mark(args, it1, 3);
-                const uint32_t d = tmem_base + acc1_col + b1 * C;
-                uint32_t accumulate = 0;
-                for (int c = 0; c < args.n_chunks; ++c) {
-                    uint32_t a_lo = x_lo0 + sx * xslot_u + c * panel_u;
-                    const uint32_t b_lo = w1_lo0 + c * args.n_taps * btile_u;
-                    for (int tap = 0; tap < args.n_taps; ++tap) {
-                        issue(d, a_lo, b_lo + tap * btile_u, accumulate);
-                        accumulate = 1;
-                        a_lo += tap1_u;
-                    }
-                }
-                umma_commit(&x_empty[sx]);
-                umma_commit(&acc1_full[b1]);
-                tlp_mark(args, it1++, 4);
-                if (++sx == args.x_slots) { sx = 0; pxl ^= 1; }
-                b1 ^= 1;
-            };
-            auto conv2 = [&] {
-                mbar_wait(&tt_full[st], (ptt >> st) & 1u, args.err_flag, 306);
-                mbar_wait(&acc2_empty[b2], (pe2 >> b2) & 1u, args.err_flag, 307);
-                pe2 ^= 1u << b2;
-                tc_fence_after();
-                tlp_mark(args, it2, 5);
-                const uint32_t d = tmem_base + acc2_col + b2 * C;
-                uint32_t accumulate = 0;
-                for (int c = 0; c < args.n_chunks; ++c) {
-                    uint32_t a_lo = tt_lo0 + st * ttslot_u + c * ttp_u;
-                    for (int tap = 0; tap < args.n_taps; ++tap) {
-                        uint32_t b_lo;
-                        if (args.w2_resident) {
-                            b_lo = w2_lo0 + (c * args.n_taps + tap) * btile_u;
-                        } else {
-                            mbar_wait(&full_b[sb], pb, args.err_flag, 308);
-                            tc_fence_after();
-                            b_lo = w2_lo0 + sb * btile_u;
-                        }
-                        issue(d, a_lo, b_lo, accumulate);
-                        accumulate = 1;
-                        a_lo += row_u;
-                        if (!args.w2_resident) {
-                            umma_commit(&empty_b[sb]);
-                            if (++sb == args.b_stages) { sb = 0; pb ^= 1; }
+            if (warp == 1) {
+                const uint32_t x_lo0 = (smem_u32(smem_x) & 0x3FFFFu) >> 4;
+                const uint32_t w1_lo0 = (smem_u32(smem_w1) & 0x3FFFFu) >> 4;
+                const uint32_t panel_u = panel_bytes >> 4, xslot_u = xslot_bytes >> 4;
+                const uint32_t tap1_u = args.dil * row_u;
+                int sx = 0, b1 = 0, it = 0;
+                uint32_t pxl = 0, pe1 = 3;   // xl_full parity; per-buffer parity bits of acc1_empty (first lap passes)
+                for (int idx = blockIdx.x; idx < args.n_work; idx += grid, ++it) {
+                    mbar_wait(&xl_full[sx], pxl, args.err_flag, 304);
+                    mbar_wait(&acc1_empty[b1], (pe1 >> b1) & 1u, args.err_flag, 305);
+                    pe1 ^= 1u << b1;
+                    tc_fence_after();
+                    tlp_mark(args, it, 3);
+                    const uint32_t d = tmem_base + acc1_col + b1 * C;
+                    uint32_t accumulate = 0;
+                    uint32_t b_lo = w1_lo0;
+                    for (int c = 0; c < args.n_chunks; ++c) {
+                        uint32_t a_lo = x_lo0 + sx * xslot_u + c * panel_u;
+                        for (int tap = 0; tap < args.n_taps; ++tap) {
+                            issue(d, a_lo, b_lo, accumulate);
+                            accumulate = 1;
+                            a_lo += tap1_u;
+                            b_lo += btile_u;
                         }
                     }
+                    umma_commit(&x_empty[sx]);
+                    umma_commit(&acc1_full[b1]);
+                    tlp_mark(args, it, 4);
+                    if (++sx == args.x_slots) { sx = 0; pxl ^= 1; }
+                    b1 ^= 1;
                 }
-                umma_commit(&tt_empty[st]);
-                umma_commit(&acc2_full[b2]);
-                tlp_mark(args, it2++, 6);
-                ptt ^= 1u << st;
-                if (args.tt_slots == 2) st ^= 1;
-                b2 ^= 1;
-            };
-            bool first = true;
-            for (int idx = blockIdx.x; idx < args.n_work; idx += grid) {
-                conv1();
-                if (!first) conv2();
-                first = false;
+            } else {
+                const uint32_t tt_lo0 = (smem_u32(smem_tt) & 0x3FFFFu) >> 4;
+                const uint32_t w2_lo0 = (smem_u32(smem_w2) & 0x3FFFFu) >> 4;
+                const uint32_t ttp_u = ttp_bytes >> 4, ttslot_u = ttslot_bytes >> 4;
+                int st = 0, sb = 0, b2 = 0, it = 0;
+                uint32_t ptt = 0, pb = 0, pe2 = 3;
+                for (int idx = blockIdx.x; idx < args.n_work; idx += grid, ++it) {
+                    mbar_wait(&tt_full[st], (ptt >> st) & 1u, args.err_flag, 306);
+                    mbar_wait(&acc2_empty[b2], (pe2 >> b2) & 1u, args.err_flag, 307);
+                    pe2 ^= 1u << b2;
+                    tc_fence_after();
+                    tlp_mark(args, it, 5);
+                    const uint32_t d = tmem_base + acc2_col + b2 * C;
+                    uint32_t accumulate = 0;
+                    uint32_t b_res = w2_lo0;
+                    for (int c = 0; c < args.n_chunks; ++c) {
+                        uint32_t a_lo = tt_lo0 + st * ttslot_u + c * ttp_u;
+                        for (int tap = 0; tap < args.n_taps; ++tap) {
+                            uint32_t b_lo = b_res;
+                            if (!args.w2_resident) {
+                                mbar_wait(&full_b[sb], pb, args.err_flag, 308);
+                                tc_fence_after();
+                                b_lo = w2_lo0 + sb * btile_u;
+                            }
+                            issue(d, a_lo, b_lo, accumulate);
+                            accumulate = 1;
+                            a_lo += row_u;
+                            b_res += btile_u;
+                            if (!args.w2_resident) {
+                                umma_commit(&empty_b[sb]);
+                                if (++sb == args.b_stages) { sb = 0; pb ^= 1; }
+                            }
+                        }
+                    }
+                    umma_commit(&tt_empty[st]);
+                    umma_commit(&acc2_full[b2]);
+                    tlp_mark(args, it, 6);
+                    ptt ^= 1u << st;
+                    if (args.tt_slots == 2) st ^= 1;
+                    b2 ^= 1;
+                }
             }
-            if (!first) conv2();
         }
-    } else if (warp < 4) {
-        // ---------------- lrelu transform, in place on the landed x panel ----------------
-        const int tid = threadIdx.x - 64;
+    } else if (warp >= 12) {
+        // ---------------- lrelu transform, in place on the landed x panel (4 warps) ----------------
+        const int tid = threadIdx.x - 12 * 32;
         const __half2 slope2 = __float2half2_rn(args.slope);
         const int units = xslot_bytes >> 4;
         int sx = 0, it = 0;
@@ -287,7 +283,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             mbar_wait(&x_full[sx], px, args.err_flag, 309);
             if (tid == 0) tlp_mark(args, it, 1);
             const uint32_t base = smem_u32(smem_x + sx * xslot_bytes);
-            for (int i = tid; i < units; i += 64) {
+            for (int i = tid; i < ((args.debug & 1) ? 0 : units); i += 128) {
                 uint4 v = lds128(base + i * 16);
                 v.x = lrelu_h2(v.x, slope2); v.y = lrelu_h2(v.y, slope2);
                 v.z = lrelu_h2(v.z, slope2); v.w = lrelu_h2(v.w, slope2);
@@ -339,7 +335,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         const float y = v[g * 8 + j] + bs[j];
                         a[j] = valid ? (y > 0.f ? y : y * slope) : 0.f;
                     }
-                    sts128(tt_base + chunk * ttp_bytes + ((u0 + g) ^ phase) * 16, pack8(a));
+                    if (!(args.debug & 2)) sts128(tt_base + chunk * ttp_bytes + ((u0 + g) ^ phase) * 16, pack8(a));
                 }
             }
             tc_fence_before();
@@ -393,8 +389,13 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             const int nt0 = nvalid ? (nidx - nb * args.tiles_t) * args.m_out : 0;
             const int nw0 = nt0 + q * 32;
             RowIO nio{stage, lane, min(32, max(0, min(args.T, nt0 + args.m_out) - nw0))};
-            lean_prefetch(args.epi, nio, static_cast<long>(nb) * args.T + nw0, 0, nvalid, pre_nxt);
-            run_epilogue_lean<kMrf>(args.epi, acc, b, t, 0, C, wait_acc, drained, stage, pre_cur, t0 + args.m_out);
+            if (args.debug & 4) {
+                wait_acc();
+                drained();
+            } else {
+                lean_prefetch(args.epi, nio, static_cast<long>(nb) * args.T + nw0, 0, nvalid, pre_nxt);
+                run_epilogue_lean<kMrf>(args.epi, acc, b, t, 0, C, wait_acc, drained, stage, pre_cur, t0 + args.m_out);
+            }
             pre_cur = pre_nxt;
             if (tl_on) tlp_mark(args, it, 12);
             pf ^= 1u << b2;
@@ -419,7 +420,7 @@ ConvPairPlan conv_pair_plan(const ConvLayer& L1, const ConvLayer& L2) {
     const int C = L1.n_total;
     if (L1.cin != C || L2.cin != C || L2.n_total != C || L1.n_tile != C || L2.n_tile != C) return p;
     if (L1.n_taps != L2.n_taps || L1.n_taps % 2 != 1 || L1.chunk_k != L2.chunk_k) return p;
-    if (C % 32 != 0 || 4 * C > 512 || C % L1.chunk_k != 0) return p;
+    if ((C != 32 && C != 64 && C != 128) || L1.chunk_k != (C == 32 ? 32 : 64)) return p;
     const int k = L1.n_taps, h2 = (k - 1) / 2;
     const int dil = k > 1 ? L1.tap_off[0][1] - L1.tap_off[0][0] : 1;
     for (int i = 0; i < k; ++i) {
@@ -501,6 +502,8 @@ int conv_pair_forward(const ConvLayer& L1, const ConvLayer& L2, const ConvPairPl
     a.slope = slope;
     a.err_flag = rt.err_flag;
     a.timeline = rt.timeline;
+    static const int debug = getenv("TTSB_PAIR_DEBUG") ? atoi(getenv("TTSB_PAIR_DEBUG")) : 0;
+    a.debug = debug;
     epi.T = T;
     epi.n_total = plan.C;
     epi.bias = L2.bias;

@@ -379,6 +379,10 @@ __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc&
     Chunk32 res_cur = pre.res, mrf_cur;
     if (kMrf) mrf_cur = pre.mrf;
     wait_acc();
+    // warp-uniform shortcuts: tiles without masked rows skip the selects, layers without an activated copy
+    // (conv_pair steps, MRF accumulation) skip its math
+    const bool any_masked = __any_sync(0xffffffffu, !in_len);
+    const bool want_act = e.out_act != nullptr && !mrf_store;
     for (int c0 = 0; c0 < n_tile; c0 += 32) {
         float v[32];
         Chunk32 res_nxt, mrf_nxt;
@@ -393,26 +397,33 @@ __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc&
         Chunk32 o_raw, o_act;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-            float r[8], m[8], bs[8], x[8], a[8];
+            float r[8], m[8], bs[8], x[8];
             unpack8(res_cur.q[g], r);
             if (kMrf) unpack8(mrf_cur.q[g], m);
             bias8(e.bias, n_base + c0 + g * 8, bs);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float y = v[g * 8 + j] + bs[j] + r[j];
-                y = in_len ? y : 0.f;
-                if (kMrf) y = m[j] + y * mscale;
-                x[j] = y;
-                a[j] = y > 0.f ? y : y * slope;
+            for (int j = 0; j < 8; ++j) x[j] = v[g * 8 + j] + bs[j] + r[j];
+            if (any_masked) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = in_len ? x[j] : 0.f;
+            }
+            if (kMrf) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = m[j] + x[j] * mscale;
             }
             o_raw.q[g] = pack8(x);
-            o_act.q[g] = pack8(a);
+            if (want_act) {
+                float a[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[j] = x[j] > 0.f ? x[j] : x[j] * slope;
+                o_act.q[g] = pack8(a);
+            }
         }
         if (mrf_store) {
             io.store(mrf_blk + c0, e.n_total, o_raw);
         } else {
             if (e.out_raw) io.store(e.out_raw + row0 * e.ld_raw + n_base + c0, e.ld_raw, o_raw);
-            if (e.out_act) io.store(e.out_act + row0 * e.ld_act + n_base + c0, e.ld_act, o_act);
+            if (want_act) io.store(e.out_act + row0 * e.ld_act + n_base + c0, e.ld_act, o_act);
         }
         res_cur = res_nxt;
         if (kMrf) mrf_cur = mrf_nxt;
