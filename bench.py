@@ -27,6 +27,10 @@ if REPO not in sys.path:
 HOP = 256
 FRAMES_PER_PHONEME = 4                      # const-4 duration head (SURVEY.md §8c calibration)
 VOCODER_FLOP_PER_FRAME = 614.1e6
+# dram__bytes_read.sum + dram__bytes_write.sum over the generator launches of one 32768-frame chunk, from the
+# `ncu --set full` capture profiles/r01_s24_ncu_full_b64.csv (70.64 GB / 32768 frames); bench.py cannot read DRAM
+# counters itself, so `roofline.traffic` = this per-frame figure x the frames of a step
+VOCODER_DRAM_BYTES_PER_FRAME = 70.64e9 / 32768
 FASTPITCH_FLOP_PER_UTT_128 = 28.8e9         # SURVEY.md §8d (L=128 -> T=512)
 
 
@@ -278,6 +282,9 @@ def run_ours(args):
     peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)' if peaks else 'fallback (B200_PROFILING.md sustained)'
     voc_flops = VOCODER_FLOP_PER_FRAME * B * T * args.steps
     achieved_tf = voc_flops / (voc_total_ms * 1e-3) / 1e12 if voc_total_ms > 0 else 0.0
+    voc_traffic = VOCODER_DRAM_BYTES_PER_FRAME * B * T            # bytes per step (rank 0)
+    peak_hbm = peaks.get('hbm_gbs', 6650.0)
+    hbm_gbs = voc_traffic * args.steps / (voc_total_ms * 1e-3) / 1e9 if voc_total_ms > 0 else 0.0
     line = {
         'metric': 'audio_samples_per_sec', 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': max(args.warmup, 3), 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak',
@@ -293,10 +300,14 @@ def run_ours(args):
                 'd2h_bytes_per_step': B * T * HOP * 4, 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': int(launches),
         'clocks': clocks,
-        'roofline': {'kernel': 'conv_tc_kernel (all HiFi-GAN generator launches of a step, rank 0)', 'bound': 'tensor',
+        'roofline': {'kernel': 'conv_tc2_kernel + conv_pair_kernel (tcgen05 row-GEMM-with-taps; all HiFi-GAN generator '
+                               'launches of a step, rank 0)', 'bound': 'tensor',
                      'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved_tf / peak_tf,
-                     'peak_source': peak_src, 'traffic': None, 'ms_per_step': voc_total_ms / args.steps,
-                     'share_of_step': voc_total_ms / ms_dev if ms_dev > 0 else None},
+                     'peak_source': peak_src, 'traffic': voc_traffic,
+                     'traffic_source': 'profiles/r01_s24_ncu_full_b64.csv (ncu --set full, dram read+write, per frame x frames)',
+                     'flops_per_step': voc_flops / args.steps, 'ms_per_step': voc_total_ms / args.steps,
+                     'share_of_step': voc_total_ms / ms_dev if ms_dev > 0 else None,
+                     'hbm': {'achieved': hbm_gbs, 'peak': peak_hbm, 'unit': 'GB/s', 'frac': hbm_gbs / peak_hbm}},
     }
     if world == 1 and not args.no_cpu_baseline:
         cores = min(usable_cores(), 32)     # torch CPU convs at batch 1 stop scaling well before this
