@@ -182,6 +182,17 @@ int ttsb_conv1d_cin_pad(const ttsb_conv1d_t* h);
 int ttsb_conv1d_forward(ttsb_conv1d_t* h, const void* d_in, int B, int T, const void* d_residual,
                         float act_slope, const int32_t* d_lens, void* d_out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * HiFi-GAN bias denoiser on a padded batch (replaces Denoiser.forward, vocoder/hifigan/denoiser.py:66-72, called
+ * once per utterance by models/fastpitch/networks.py:343-344): STFT(1024, hop 256, periodic hann, center/reflect)
+ * -> max(|X| - strength * bias_spec, 0) * exp(j arg X) -> ISTFT, each utterance at its OWN length
+ * d_n_samples[b] (multiples of 256; samples beyond it are written as zeros).
+ * d_wav / d_out: [B, n_max] fp32; d_bias_spec: [513] fp32 (Denoiser.bias_spec); workspace: frame buffer.
+ * --------------------------------------------------------------------------------------------- */
+size_t ttsb_denoiser_workspace_bytes(int B, int n_max);
+int ttsb_denoiser_forward(const float* d_wav, const int32_t* d_n_samples, int B, int n_max, const float* d_bias_spec,
+                          float strength, float* d_out, void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* Op-level entry for one fused ResBlock1 step (vocoder/hifigan/models.py:46-53, one (c1, c2) iteration):
  *   out = x + conv2(lrelu(conv1(lrelu(x)) + b1)) + b2,  conv1 = Conv1d(C, C, k, dilation=d), conv2 = Conv1d(C, C, k)
  * as ONE kernel launch (csrc/conv_pair.cu). w1/w2: [C, C, k] fp32 host, b1/b2: [C]. d_x/d_out: [B, T, C] fp16

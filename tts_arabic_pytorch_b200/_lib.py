@@ -80,6 +80,9 @@ _SIGNATURES = {
     'ttsb_conv1d_cin_pad': (c_int, [c_void_p]),
     'ttsb_conv1d_forward': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p,
                                     c_void_p]),
+    'ttsb_denoiser_workspace_bytes': (c_size_t, [c_int, c_int]),
+    'ttsb_denoiser_forward': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p, c_size_t,
+                                      c_void_p]),
     'ttsb_convpair_create': (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                      ctypes.POINTER(c_void_p)]),
     'ttsb_convpair_destroy': (None, [c_void_p]),
