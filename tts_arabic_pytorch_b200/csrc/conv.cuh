@@ -84,6 +84,7 @@ struct ConvPairPlan {
     int C = 0, m_out = 0, h2 = 0, dil = 1, rows_panel = 0, tt_rows = 0;
     int x_slots = 0, tt_slots = 0, w2_resident = 0, b_stages = 0, tmem_cols = 0;
     size_t smem_bytes = 0;
+    const __half* ident = nullptr;   // device: C x C identity in the packed weight-tile layout (shared per C, never freed)
 };
 // ok = 0 when the pair does not fit the fused kernel (caller falls back to two conv_forward launches)
 ConvPairPlan conv_pair_plan(const ConvLayer& L1, const ConvLayer& L2);

@@ -80,6 +80,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
     // 4 x 2 KB staging tiles for the epilogue warps' coalesced row I/O (epilogue.cuh)
     uint8_t* smem_stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 127) & ~static_cast<uintptr_t>(127));
+    float* sbias = reinterpret_cast<float*>(smem_stage + 4 * 2048);   // [n_tile] this N tile's bias (lean epilogue: smem broadcast)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -105,6 +106,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
+    if (kEpi != 0)
+        for (int i = threadIdx.x; i < args.n_tile; i += 192)
+            sbias[i] = args.epi.bias != nullptr ? args.epi.bias[ntile * args.n_tile + i] : 0.f;
     tc_fence_before();
     __syncthreads();
     if (csize == 2) cluster_sync_all();   // peer barriers must be initialised before any multicast / remote arrive
@@ -270,7 +274,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             const int b0 = v0 ? idx0 / args.groups_t : 0;
             const int w0 = (v0 ? (idx0 - b0 * args.groups_t) * args.rpp : args.groups_t * args.rpp) * kTileM + q * 32;
             RowIO io{stage, lane, min(32, max(0, args.T - w0))};
-            lean_prefetch(args.epi, io, static_cast<long>(b0) * args.T + w0, n_base, v0, pre_cur);
+            lean_prefetch(args.epi, io, static_cast<long>(b0) * args.T + w0, n_base, v0, pre_cur, b0);
         }
         for (int p = first; p < n_groups; p += stride, ++tl_i) {
             const int idx = p * csize + crank;
@@ -307,8 +311,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     const int nw0 = ((nvalid ? (nidx - nb * args.groups_t) * args.rpp : args.groups_t * args.rpp) +
                                      (last_r ? 0 : r + 1)) * kTileM + q * 32;
                     RowIO nio{stage, lane, min(32, max(0, args.T - nw0))};
-                    lean_prefetch(args.epi, nio, static_cast<long>(nb) * args.T + nw0, n_base, nvalid, pre_nxt);
-                    run_epilogue_lean<kMrf>(args.epi, acc, b, t, n_base, args.n_tile, wait_acc, drained, stage, pre_cur);
+                    lean_prefetch(args.epi, nio, static_cast<long>(nb) * args.T + nw0, n_base, nvalid, pre_nxt, nb);
+                    run_epilogue_lean<kMrf, true>(args.epi, acc, b, t, n_base, args.n_tile, wait_acc, drained, stage, pre_cur,
+                                            0x7fffffff, smem_u32(sbias));
                     pre_cur = pre_nxt;
                 } else {
                     long long* dbg = (tl_on && args.timeline != nullptr && blockIdx.x < 256 && tl_i < 7)

@@ -180,6 +180,14 @@ __device__ __forceinline__ void bias8(const float* bias, int n, float (&f)[8]) {
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
 
+// same from shared memory (a broadcast read): with ~all of the SM's L1 carved out as shared memory the __ldg path
+// above misses to L2 — one ~700-cycle round trip per 8 columns, on the epilogue's critical path
+__device__ __forceinline__ void bias8s(uint32_t saddr, float (&f)[8]) {
+    // not volatile: the bias tile is written once before the role dispatch, so the compiler may hoist / batch these
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]) : "r"(saddr));
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7]) : "r"(saddr + 16));
+}
+
 // b: utterance, t: row inside the utterance (lane i of the warp owns row t = warp_row0 + i), row_ok:
 // t < T (loads from the accumulator are warp-collective, so out-of-range threads still walk the loop
 // but never touch memory). n_base: first logical column of this N tile; n_tile: its width (multiple
@@ -346,10 +354,12 @@ template <bool kMrf>
 struct LeanPrefetch {
     Chunk32 res;
     Chunk32 mrf;   // only live when kMrf (otherwise never touched, so it costs no registers)
+    int len_rows;  // valid rows of the tile's utterance (lens[b] * len_mul), fetched a tile ahead: it is an L2 round trip
 };
 template <bool kMrf>
 __device__ __forceinline__ void lean_prefetch(const EpiParams& e, const RowIO& io, long row0, int n_base, bool on,
-                                              LeanPrefetch<kMrf>& p) {
+                                              LeanPrefetch<kMrf>& p, int b) {
+    p.len_rows = (on && e.lens != nullptr) ? __ldg(e.lens + b) * e.len_mul : 0x7fffffff;
     io.request(e.residual + row0 * e.ld_res + n_base, e.ld_res, on && e.residual != nullptr, p.res);
     if (kMrf) {
         const bool use_mrf = e.mrf_mode == MRF_ADD || e.mrf_mode == MRF_LAST;
@@ -358,15 +368,17 @@ __device__ __forceinline__ void lean_prefetch(const EpiParams& e, const RowIO& i
 }
 
 // kMrf = false: mrf_mode == MRF_NONE is guaranteed by the caller.
-template <bool kMrf, class Acc, class WaitFn, class DrainFn>
+template <bool kMrf, bool kSmemBias = false, class Acc, class WaitFn, class DrainFn>
 __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc& acc, int b, int t, int n_base,
                                                   int n_tile, WaitFn wait_acc, DrainFn acc_drained, uint8_t* stage,
-                                                  const LeanPrefetch<kMrf>& pre, int t_end = 0x7fffffff) {
+                                                  const LeanPrefetch<kMrf>& pre, int t_end = 0x7fffffff,
+                                                  uint32_t bias_saddr = 0) {
+    // kSmemBias: bias_saddr is the shared-memory address of this N tile's bias floats (else e.bias through __ldg)
     // t_end: exclusive row limit of this tile's stores (conv_pair tiles own fewer than 128 rows)
     const int lane = threadIdx.x & 31;
     const int warp_row0 = t - lane;
     const long row0 = static_cast<long>(b) * e.T + warp_row0;
-    const bool in_len = e.lens == nullptr || t < __ldg(e.lens + b) * e.len_mul;
+    const bool in_len = t < pre.len_rows;
     RowIO io{stage, lane, min(32, max(0, min(e.T, t_end) - warp_row0))};
     const bool use_res = e.residual != nullptr;
     const bool use_mrf = kMrf && (e.mrf_mode == MRF_ADD || e.mrf_mode == MRF_LAST);
@@ -400,7 +412,8 @@ __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc&
             float r[8], m[8], bs[8], x[8];
             unpack8(res_cur.q[g], r);
             if (kMrf) unpack8(mrf_cur.q[g], m);
-            bias8(e.bias, n_base + c0 + g * 8, bs);
+            if (kSmemBias) bias8s(bias_saddr + (c0 + g * 8) * 4, bs);
+            else bias8(e.bias, n_base + c0 + g * 8, bs);
 #pragma unroll
             for (int j = 0; j < 8; ++j) x[j] = v[g * 8 + j] + bs[j] + r[j];
             if (any_masked) {
