@@ -37,14 +37,18 @@ int launch_pack_mel(const float* mel, const int* lens, int B, int C, int T, __ha
 }
 
 // ------------------------------------------------------------------------------------------------
-// conv_post + tanh: 256 samples per block, (256+6) x 32 activations staged in smem (pitch 33)
+// conv_post + tanh: 256 samples per block. The (256+6) x 32 fp16 activations are staged as they are (80-byte row
+// pitch: 16-byte reads of consecutive rows hit disjoint banks), the 7 x 32 weights as fp32; a thread reads its
+// 7 rows with 4 LDS.128 each and the weights with broadcast LDS.128 — 84 shared loads for 224 FMAs (the first
+// version staged fp32 and issued two 4-byte loads per FMA, which made it LSU-bound at 1.3 TB/s).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) conv_post_tanh_kernel(const __half* __restrict__ x,
                                                              const float* __restrict__ w, float bias,
                                                              const int* __restrict__ lens, int len_mul,
                                                              int N, float* __restrict__ wav) {
-    __shared__ float sx[262 * 33];
-    __shared__ float sw[7 * 32];
+    constexpr int kPitch = 80;                       // bytes per staged row (64 B of data)
+    __shared__ __align__(16) uint8_t sx[262 * kPitch];
+    __shared__ __align__(16) float sw[7 * 32];
     const int b = blockIdx.y;
     const int n0 = blockIdx.x * 256;
     if (threadIdx.x < 224) sw[threadIdx.x] = w[threadIdx.x];
@@ -52,10 +56,9 @@ __global__ void __launch_bounds__(256) conv_post_tanh_kernel(const __half* __res
     for (int i = threadIdx.x; i < 262 * 4; i += 256) {
         const int r = i >> 2, q = i & 3;
         const int n = n0 + r - 3;
-        float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (n >= 0 && n < N) load8h(x + (static_cast<size_t>(b) * N + n) * 32 + q * 8, f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) sx[r * 33 + q * 8 + j] = f[j];
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (n >= 0 && n < N) v = *reinterpret_cast<const uint4*>(x + (static_cast<size_t>(b) * N + n) * 32 + q * 8);
+        *reinterpret_cast<uint4*>(sx + r * kPitch + q * 16) = v;
     }
     __syncthreads();
     const int n = n0 + threadIdx.x;
@@ -63,9 +66,15 @@ __global__ void __launch_bounds__(256) conv_post_tanh_kernel(const __half* __res
     float acc = bias;
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
-        const float* row = sx + (threadIdx.x + k) * 33;
+        const uint8_t* row = sx + (threadIdx.x + k) * kPitch;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) acc += row[c] * sw[k * 32 + c];
+        for (int q = 0; q < 4; ++q) {
+            float f[8];
+            unpack8(*reinterpret_cast<const uint4*>(row + q * 16), f);
+            const float4 w0 = *reinterpret_cast<const float4*>(sw + k * 32 + q * 8);
+            const float4 w1 = *reinterpret_cast<const float4*>(sw + k * 32 + q * 8 + 4);
+            acc += f[0] * w0.x + f[1] * w0.y + f[2] * w0.z + f[3] * w0.w + f[4] * w1.x + f[5] * w1.y + f[6] * w1.z + f[7] * w1.w;
+        }
     }
     const int len = lens ? lens[b] * len_mul : N;
     wav[static_cast<size_t>(b) * N + n] = n < len ? tanhf(acc) : 0.f;
