@@ -43,6 +43,7 @@ struct ConvTc2Args {
     int step[2];       // off(tap+1) - off(tap)
     int halo_lo;
     const __half* w;
+    int params_smem;   // general epilogue: [bias][ln_g][ln_b][head_w] of this N tile staged in shared memory (room permitting)
     int* err_flag;
     long long* timeline;   // debug (tools/timeline.py): 64 clock64() slots per CTA for the first 256 CTAs, or null
     EpiParams epi;
@@ -106,9 +107,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
-    if (kEpi != 0)
+    if (kEpi != 0) {
         for (int i = threadIdx.x; i < args.n_tile; i += 192)
             sbias[i] = args.epi.bias != nullptr ? args.epi.bias[ntile * args.n_tile + i] : 0.f;
+    } else if (args.params_smem) {
+        const float* src[4] = {args.epi.bias, args.epi.ln_g, args.epi.ln_b, args.epi.head_w};
+        for (int i = threadIdx.x; i < 4 * args.n_tile; i += 192) {
+            const float* p = src[i / args.n_tile];
+            sbias[i] = p != nullptr ? p[ntile * args.n_tile + i % args.n_tile] : 0.f;
+        }
+    }
     tc_fence_before();
     __syncthreads();
     if (csize == 2) cluster_sync_all();   // peer barriers must be initialised before any multicast / remote arrive
@@ -318,7 +326,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 } else {
                     long long* dbg = (tl_on && args.timeline != nullptr && blockIdx.x < 256 && tl_i < 7)
                                          ? args.timeline + blockIdx.x * 128 + 64 + tl_i * 8 : nullptr;
-                    run_epilogue(args.epi, acc, b, t, t < args.T, n_base, args.n_tile, wait_acc, drained, stage, dbg);
+                    run_epilogue(args.epi, acc, b, t, t < args.T, n_base, args.n_tile, wait_acc, drained, stage, dbg,
+                                 args.params_smem ? smem_u32(sbias) : 0u);
                 }
             }
             if (tl_on && tl_i < 7) tl2_mark(args, 8 + tl_i * 8 + 6);
@@ -479,6 +488,19 @@ int conv_forward_tc2(const ConvLayer& L, const ConvRuntime& rt, const __half* in
     a.w = L.w_packed; a.err_flag = rt.err_flag; a.epi = epi;
     a.timeline = rt.timeline;
 
+    // general epilogue with LayerNorm: stage the per-column parameters in shared memory when the plan leaves room
+    // (2 KB are always reserved for the lean epilogue's bias tile)
+    a.params_smem = 0;
+    size_t smem_bytes = L.smem_bytes2;
+    if (!host_epi_is_lean(epi) && epi.ln_g != nullptr) {
+        const size_t need = 4 * static_cast<size_t>(L.n_tile) * sizeof(float);
+        const size_t extra = need > 2048 ? need - 2048 : 0;
+        const size_t limit = 233472 / L.occ2 - 1024;
+        if (L.smem_bytes2 + extra <= limit && L.smem_bytes2 + extra <= 232448) {
+            a.params_smem = 1;
+            smem_bytes += extra;
+        }
+    }
     // CTA pairs share streamed weight tiles through TMA multicast (halves the L2->SM weight traffic that
     // bounds the C >= 128 layers); needs at least two work items per N tile
     static const int want_cluster = getenv("TTSB_CLUSTER") ? atoi(getenv("TTSB_CLUSTER")) : 2;
@@ -493,27 +515,27 @@ int conv_forward_tc2(const ConvLayer& L, const ConvRuntime& rt, const __half* in
     // the register cap follows the planned CTAs per SM (1: 255, 2: 168, 3: 112 registers per thread)
     if (L.occ2 >= 3) {
         switch (L.tmem_cols2) {
-            case 32: return launch_two<32, 3>(tm, a, ctas, L.smem_bytes2, stream);
-            case 64: return launch_two<64, 3>(tm, a, ctas, L.smem_bytes2, stream);
-            case 128: return launch_two<128, 3>(tm, a, ctas, L.smem_bytes2, stream);
+            case 32: return launch_two<32, 3>(tm, a, ctas, smem_bytes, stream);
+            case 64: return launch_two<64, 3>(tm, a, ctas, smem_bytes, stream);
+            case 128: return launch_two<128, 3>(tm, a, ctas, smem_bytes, stream);
         }
         TTSB_REQUIRE(false, "occupancy 3 needs <= 128 TMEM columns");
     }
     if (L.occ2 == 2) {
         switch (L.tmem_cols2) {
-            case 32: return launch_two<32, 2>(tm, a, ctas, L.smem_bytes2, stream);
-            case 64: return launch_two<64, 2>(tm, a, ctas, L.smem_bytes2, stream);
-            case 128: return launch_two<128, 2>(tm, a, ctas, L.smem_bytes2, stream);
-            case 256: return launch_two<256, 2>(tm, a, ctas, L.smem_bytes2, stream);
+            case 32: return launch_two<32, 2>(tm, a, ctas, smem_bytes, stream);
+            case 64: return launch_two<64, 2>(tm, a, ctas, smem_bytes, stream);
+            case 128: return launch_two<128, 2>(tm, a, ctas, smem_bytes, stream);
+            case 256: return launch_two<256, 2>(tm, a, ctas, smem_bytes, stream);
         }
         TTSB_REQUIRE(false, "occupancy 2 needs <= 256 TMEM columns");
     }
     switch (L.tmem_cols2) {
-        case 32: return launch_two<32, 1>(tm, a, ctas, L.smem_bytes2, stream);
-        case 64: return launch_two<64, 1>(tm, a, ctas, L.smem_bytes2, stream);
-        case 128: return launch_two<128, 1>(tm, a, ctas, L.smem_bytes2, stream);
-        case 256: return launch_two<256, 1>(tm, a, ctas, L.smem_bytes2, stream);
-        case 512: return launch_two<512, 1>(tm, a, ctas, L.smem_bytes2, stream);
+        case 32: return launch_two<32, 1>(tm, a, ctas, smem_bytes, stream);
+        case 64: return launch_two<64, 1>(tm, a, ctas, smem_bytes, stream);
+        case 128: return launch_two<128, 1>(tm, a, ctas, smem_bytes, stream);
+        case 256: return launch_two<256, 1>(tm, a, ctas, smem_bytes, stream);
+        case 512: return launch_two<512, 1>(tm, a, ctas, smem_bytes, stream);
     }
     TTSB_REQUIRE(false, "bad tmem_cols");
     return 1;

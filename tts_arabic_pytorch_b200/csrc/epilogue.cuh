@@ -199,7 +199,9 @@ template <class Acc, class WaitFn, class DrainFn>
 __device__ __forceinline__ void run_epilogue(const EpiParams& e, const Acc& acc, int b, int t,
                                              bool row_ok, int n_base, int n_tile, WaitFn wait_acc,
                                              DrainFn acc_drained, uint8_t* stage = nullptr,
-                                             long long* dbg = nullptr) {
+                                             long long* dbg = nullptr, uint32_t params_saddr = 0) {
+    // params_saddr != 0: shared-memory copy of this N tile's per-column parameters, n_tile floats each:
+    // [bias][ln_g][ln_b][head_w] (see bias8s for why)
     const int lane = threadIdx.x & 31;
     const int warp_row0 = t - lane;
     const long row0 = static_cast<long>(b) * e.T + warp_row0;      // first row of this warp
@@ -213,6 +215,11 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& e, const Acc& acc,
     const __half* res_blk = e.residual + row0 * e.ld_res + n_base;
     __half* mrf_blk = e.mrf_buf + row0 * e.n_total + n_base;
 
+    // which = 0 bias, 1 ln_g, 2 ln_b, 3 head_w; n = global column
+    auto param8 = [&](int which, const float* gptr, int n, float (&f)[8]) {
+        if (params_saddr != 0 && gptr != nullptr) bias8s(params_saddr + (which * n_tile + (n - n_base)) * 4, f);
+        else bias8(gptr, n, f);
+    };
     Chunk32 res_cur, mrf_cur;
     io.request(res_blk, e.ld_res, use_res, res_cur);
     io.request(mrf_blk, e.n_total, use_mrf, mrf_cur);
@@ -235,7 +242,7 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& e, const Acc& acc,
                 for (int g = 0; g < 4; ++g) {
                     float r[8], bs[8];
                     unpack8(res_cur.q[g], r);
-                    bias8(e.bias, n_base + c0 + g * 8, bs);
+                    param8(0, e.bias, n_base + c0 + g * 8, bs);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         float x = v[g * 8 + j] + bs[j] + r[j];
@@ -277,20 +284,20 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& e, const Acc& acc,
             float x[8];
             if (do_ln) {
                 float gm[8], bt[8];
-                bias8(e.ln_g, n, gm);
-                bias8(e.ln_b, n, bt);
+                param8(1, e.ln_g, n, gm);
+                param8(2, e.ln_b, n, bt);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) x[j] = (v[g * 8 + j] - mean) * rstd * gm[j] + bt[j];
                 if (e.head_w) {
                     float hw[8];
-                    bias8(e.head_w, n, hw);
+                    param8(3, e.head_w, n, hw);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) head += x[j] * hw[j];
                 }
             } else {
                 float r[8], bs[8];
                 unpack8(res_cur.q[g], r);
-                bias8(e.bias, n, bs);
+                param8(0, e.bias, n, bs);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) x[j] = v[g * 8 + j] + bs[j] + r[j];
             }
