@@ -1,5 +1,7 @@
 // HBM-bound and small kernels: layout packing, embedding, attention, length regulation,
 // conv_post+tanh. See kernels.cuh for the reference op site each one replaces.
+#include <cstdlib>
+#include <string>
 #include "kernels.cuh"
 #include "epilogue.cuh"
 
@@ -247,16 +249,168 @@ __global__ void __launch_bounds__(256) attention_kernel(const __half* __restrict
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// attention on the legacy tensor path (mma.sync m16n8k16, fp16 in / fp32 accumulate): the same online-softmax
+// schedule, 64 queries per CTA as 4 warps x 16 rows, K/V tiles of 64 keys staged with a 144-byte row pitch
+// (conflict-free ldmatrix). 2 % of the model's FLOPs with S <= ~1k and d_head = 64: a tcgen05 tile (M = 128,
+// TMEM round trip for the softmax) does not pay here; the fp32-FMA kernel above stays as the cross-check
+// (TTSB_ATTENTION=simt).
+// ------------------------------------------------------------------------------------------------
+constexpr int kAttPitch = 72;   // halfs per staged row (64 of data)
+
+__device__ __forceinline__ void ldsm_x4(uint32_t saddr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t saddr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(128) attention_mma_kernel(const __half* __restrict__ qkv,
+                                                            const int* __restrict__ lens, int S,
+                                                            float scale, __half* __restrict__ out) {
+    __shared__ __align__(16) __half sq[64 * kAttPitch];
+    __shared__ __align__(16) __half sk[64 * kAttPitch];
+    __shared__ __align__(16) __half sv[64 * kAttPitch];
+    const int b = blockIdx.y;
+    const int q0 = blockIdx.x * 64;
+    const int len = lens ? min(lens[b], S) : S;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const __half* base = qkv + static_cast<size_t>(b) * S * 192;
+
+    // stage Q (rows beyond S as zeros)
+    for (int i = threadIdx.x; i < 64 * 8; i += 128) {
+        const int r = i >> 3, c8 = i & 7;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (q0 + r < S) v = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(q0 + r) * 192 + c8 * 8);
+        *reinterpret_cast<uint4*>(sq + r * kAttPitch + c8 * 8) = v;
+    }
+    __syncthreads();
+    // Q fragments of this warp's 16 rows, all four k steps of d
+    uint32_t qf[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+        ldsm_x4(smem_u32(sq + (warp * 16 + (lane & 15)) * kAttPitch + ks * 16 + (lane >> 4) * 8), qf[ks]);
+
+    float o[8][4];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[nb][j] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;   // rows lane/4 and lane/4 + 8
+    const float sl2 = scale * 1.4426950408889634f;              // scores in log2 units
+
+    for (int k0 = 0; k0 < len; k0 += 64) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 64 * 8; i += 128) {
+            const int r = i >> 3, c8 = i & 7;
+            uint4 vk = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+            if (k0 + r < len) {
+                vk = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(k0 + r) * 192 + 64 + c8 * 8);
+                vv = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(k0 + r) * 192 + 128 + c8 * 8);
+            }
+            *reinterpret_cast<uint4*>(sk + r * kAttPitch + c8 * 8) = vk;
+            *reinterpret_cast<uint4*>(sv + r * kAttPitch + c8 * 8) = vv;
+        }
+        __syncthreads();
+        // S = Q K^T: 8 key blocks of 8, 4 k steps over d
+        float sc[8][4];
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sc[nb][j] = 0.f;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t kf[4];   // keys nb*8.., d = h*32 + {0-7, 8-15, 16-23, 24-31}
+                ldsm_x4(smem_u32(sk + (nb * 8 + (lane & 7)) * kAttPitch + h * 32 + (lane >> 3) * 8), kf);
+                mma_16816(sc[nb], qf[h * 2], kf[0], kf[1]);
+                mma_16816(sc[nb], qf[h * 2 + 1], kf[2], kf[3]);
+            }
+        }
+        // online softmax; thread owns cols (lane%4)*2, +1 of each key block for rows lane/4 (c0,c1) and +8 (c2,c3)
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+            const int key = k0 + nb * 8 + (lane & 3) * 2;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool ok = key + (j & 1) < len;
+                sc[nb][j] = ok ? sc[nb][j] * sl2 : -INFINITY;
+            }
+            mx0 = fmaxf(mx0, fmaxf(sc[nb][0], sc[nb][1]));
+            mx1 = fmaxf(mx1, fmaxf(sc[nb][2], sc[nb][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);   // finite: every tile has >= 1 valid key
+        const float c0 = exp2f(m0 - mn0), c1 = exp2f(m1 - mn1);
+        m0 = mn0; m1 = mn1;
+        float ps0 = 0.f, ps1 = 0.f;
+        uint32_t pf[4][4];   // P as A fragments: k step j = key blocks 2j, 2j+1
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+            const float p0 = exp2f(sc[nb][0] - mn0), p1 = exp2f(sc[nb][1] - mn0);
+            const float p2 = exp2f(sc[nb][2] - mn1), p3 = exp2f(sc[nb][3] - mn1);
+            ps0 += p0 + p1;
+            ps1 += p2 + p3;
+            pf[nb >> 1][(nb & 1) * 2 + 0] = pack_half2(p0, p1);
+            pf[nb >> 1][(nb & 1) * 2 + 1] = pack_half2(p2, p3);
+        }
+        ps0 += __shfl_xor_sync(0xffffffffu, ps0, 1);
+        ps0 += __shfl_xor_sync(0xffffffffu, ps0, 2);
+        ps1 += __shfl_xor_sync(0xffffffffu, ps1, 1);
+        ps1 += __shfl_xor_sync(0xffffffffu, ps1, 2);
+        l0 = l0 * c0 + ps0;
+        l1 = l1 * c1 + ps1;
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) { o[nb][0] *= c0; o[nb][1] *= c0; o[nb][2] *= c1; o[nb][3] *= c1; }
+        // O += P V: 4 k steps of 16 keys, 8 d blocks (two per ldmatrix.trans)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+            for (int n2 = 0; n2 < 4; ++n2) {
+                uint32_t vf[4];   // {keys 0-7, 8-15} x d block 2*n2, then the same for d block 2*n2+1
+                ldsm_x4_trans(smem_u32(sv + (ks * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * kAttPitch + (n2 * 2 + (lane >> 4)) * 8), vf);
+                mma_16816(o[n2 * 2], pf[ks], vf[0], vf[1]);
+                mma_16816(o[n2 * 2 + 1], pf[ks], vf[2], vf[3]);
+            }
+        }
+    }
+    const float inv0 = l0 > 0.f ? 1.f / l0 : 0.f, inv1 = l1 > 0.f ? 1.f / l1 : 0.f;
+    const int r0 = q0 + warp * 16 + (lane >> 2), r1 = r0 + 8;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+        const int d = nb * 8 + (lane & 3) * 2;
+        if (r0 < S) *reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(b) * S + r0) * 64 + d) = pack_half2(o[nb][0] * inv0, o[nb][1] * inv0);
+        if (r1 < S) *reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(b) * S + r1) * 64 + d) = pack_half2(o[nb][2] * inv1, o[nb][3] * inv1);
+    }
+}
+
 static const int kAttSmem = 4 * 64 * 65 * sizeof(float);
 int launch_attention(const __half* qkv, const int* lens, int B, int S, float scale, __half* out,
                      cudaStream_t s) {
+    static const bool use_simt = getenv("TTSB_ATTENTION") != nullptr && std::string(getenv("TTSB_ATTENTION")) == "simt";
+    dim3 grid(ceil_div(S, 64), B);
+    if (!use_simt) {
+        attention_mma_kernel<<<grid, 128, 0, s>>>(qkv, lens, S, scale, out);
+        count_launch();
+        TTSB_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
     static bool configured = false;
     if (!configured) {
         TTSB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              kAttSmem));
         configured = true;
     }
-    dim3 grid(ceil_div(S, 64), B);
     attention_kernel<<<grid, 256, kAttSmem, s>>>(qkv, lens, S, scale, out);
     count_launch();
     TTSB_CHECK_CUDA(cudaGetLastError());
