@@ -27,7 +27,8 @@
 
 namespace ttsb {
 
-constexpr int kPairThreads = 512;
+constexpr int kPairThreads = 512;   // 16 warps = 4 per scheduler: 128 registers per thread
+constexpr int kPairXformWarps = 4;
 constexpr int kPairMaxX = 8;
 constexpr int kPairMaxB = 8;
 
@@ -116,7 +117,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     if (warp == 0 && elect_one()) {
         if (args.timeline != nullptr && blockIdx.x < 256) args.timeline[blockIdx.x * 128] = clock64();
         tma_prefetch_desc(&tmap_x);
-        for (int i = 0; i < args.x_slots; ++i) { mbar_init(&x_full[i], 1); mbar_init(&xl_full[i], 4); mbar_init(&x_empty[i], 1); }
+        for (int i = 0; i < args.x_slots; ++i) { mbar_init(&x_full[i], 1); mbar_init(&xl_full[i], kPairXformWarps); mbar_init(&x_empty[i], 1); }
         for (int i = 0; i < args.b_stages; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tt_full[i], 4); mbar_init(&tt_empty[i], 1);
@@ -286,7 +287,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             mbar_wait(&x_full[sx], px, args.err_flag, 309);
             if (tid == 0) tlp_mark(args, it, 1);
             const uint32_t base = smem_u32(smem_x + sx * xslot_bytes);
-            for (int i = tid; i < ((args.debug & 1) ? 0 : units); i += 128) {
+            for (int i = tid; i < ((args.debug & 1) ? 0 : units); i += kPairXformWarps * 32) {
                 uint4 v = lds128(base + i * 16);
                 v.x = lrelu_h2(v.x, slope2); v.y = lrelu_h2(v.y, slope2);
                 v.z = lrelu_h2(v.z, slope2); v.w = lrelu_h2(v.w, slope2);
@@ -399,9 +400,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 wait_acc();
                 drained();
             } else {
-                lean_prefetch(args.epi, nio, static_cast<long>(nb) * args.T + nw0, 0, nvalid, pre_nxt, nb);
-                run_epilogue_lean<kMrf, true>(args.epi, acc, b, t, 0, C, wait_acc, drained, stage, pre_cur, t0 + args.m_out,
+                // the next tile's residual rows are requested before this tile's accumulator is waited for — except in
+                // the MRF variant, whose extra live chunks would spill (and a spill reload is an L2 round trip here)
+                if (!kMrf) lean_prefetch(args.epi, nio, static_cast<long>(nb) * args.T + nw0, 0, nvalid, pre_nxt, nb);
+                run_epilogue_lean<kMrf, true, !kMrf>(args.epi, acc, b, t, 0, C, wait_acc, drained, stage, pre_cur, t0 + args.m_out,
                                         smem_u32(sbias2));
+                if (kMrf) lean_prefetch(args.epi, nio, static_cast<long>(nb) * args.T + nw0, 0, nvalid, pre_nxt, nb);
             }
             pre_cur = pre_nxt;
             if (tl_on) tlp_mark(args, it, 12);

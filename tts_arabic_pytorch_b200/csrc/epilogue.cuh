@@ -360,22 +360,23 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& e, const Acc& acc,
 template <bool kMrf>
 struct LeanPrefetch {
     Chunk32 res;
-    Chunk32 mrf;   // only live when kMrf (otherwise never touched, so it costs no registers)
     int len_rows;  // valid rows of the tile's utterance (lens[b] * len_mul), fetched a tile ahead: it is an L2 round trip
 };
+// Only the residual rows travel a tile ahead. The MRF rows are requested at the start of their own tile: a second
+// prefetched chunk pair pushed the MRF variants over the register budget, and with the L1 carved out as shared
+// memory every spill reload is an L2 round trip — the spilling variants ran at HALF the speed of the others
+// (profiles/r01_s41_launches_b64.csv).
 template <bool kMrf>
 __device__ __forceinline__ void lean_prefetch(const EpiParams& e, const RowIO& io, long row0, int n_base, bool on,
                                               LeanPrefetch<kMrf>& p, int b) {
     p.len_rows = (on && e.lens != nullptr) ? __ldg(e.lens + b) * e.len_mul : 0x7fffffff;
     io.request(e.residual + row0 * e.ld_res + n_base, e.ld_res, on && e.residual != nullptr, p.res);
-    if (kMrf) {
-        const bool use_mrf = e.mrf_mode == MRF_ADD || e.mrf_mode == MRF_LAST;
-        io.request(e.mrf_buf + row0 * e.n_total + n_base, e.n_total, on && use_mrf, p.mrf);
-    }
 }
 
 // kMrf = false: mrf_mode == MRF_NONE is guaranteed by the caller.
-template <bool kMrf, bool kSmemBias = false, class Acc, class WaitFn, class DrainFn>
+// kLookahead = false (register-starved variants): a chunk's residual / MRF rows are requested when the chunk
+// starts, not one chunk ahead.
+template <bool kMrf, bool kSmemBias = false, bool kLookahead = true, class Acc, class WaitFn, class DrainFn>
 __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc& acc, int b, int t, int n_base,
                                                   int n_tile, WaitFn wait_acc, DrainFn acc_drained, uint8_t* stage,
                                                   const LeanPrefetch<kMrf>& pre, int t_end = 0x7fffffff,
@@ -396,7 +397,7 @@ __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc&
     const float slope = e.act_slope;
 
     Chunk32 res_cur = pre.res, mrf_cur;
-    if (kMrf) mrf_cur = pre.mrf;
+    if (kMrf) io.request(mrf_blk, e.n_total, use_mrf, mrf_cur);
     wait_acc();
     // warp-uniform shortcuts: tiles without masked rows skip the selects, layers without an activated copy
     // (conv_pair steps, MRF accumulation) skip its math
@@ -406,8 +407,13 @@ __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc&
         float v[32];
         Chunk32 res_nxt, mrf_nxt;
         const bool more = c0 + 32 < n_tile;
-        io.request(res_blk + c0 + 32, e.ld_res, use_res && more, res_nxt);
-        if (kMrf) io.request(mrf_blk + c0 + 32, e.n_total, use_mrf && more, mrf_nxt);
+        if (kLookahead) {
+            io.request(res_blk + c0 + 32, e.ld_res, use_res && more, res_nxt);
+            if (kMrf) io.request(mrf_blk + c0 + 32, e.n_total, use_mrf && more, mrf_nxt);
+        } else if (c0 > 0) {
+            io.request(res_blk + c0, e.ld_res, use_res, res_cur);
+            if (kMrf) io.request(mrf_blk + c0, e.n_total, use_mrf, mrf_cur);
+        }
         if (use_res) io.to_row(res_cur);
         if (kMrf && use_mrf) io.to_row(mrf_cur);
         __syncwarp();
@@ -445,8 +451,10 @@ __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc&
             if (e.out_raw) io.store(e.out_raw + row0 * e.ld_raw + n_base + c0, e.ld_raw, o_raw);
             if (want_act) io.store(e.out_act + row0 * e.ld_act + n_base + c0, e.ld_act, o_act);
         }
-        res_cur = res_nxt;
-        if (kMrf) mrf_cur = mrf_nxt;
+        if (kLookahead) {
+            res_cur = res_nxt;
+            if (kMrf) mrf_cur = mrf_nxt;
+        }
     }
 }
 #endif  // __CUDACC__
