@@ -320,7 +320,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                                      (last_r ? 0 : r + 1)) * kTileM + q * 32;
                     RowIO nio{stage, lane, min(32, max(0, args.T - nw0))};
                     lean_prefetch(args.epi, nio, static_cast<long>(nb) * args.T + nw0, n_base, nvalid, pre_nxt, nb);
-                    run_epilogue_lean<kMrf, true>(args.epi, acc, b, t, n_base, args.n_tile, wait_acc, drained, stage, pre_cur,
+                    run_epilogue_lean<kMrf, true, !(kMrf && kMinBlocks >= 2)>(args.epi, acc, b, t, n_base, args.n_tile, wait_acc, drained, stage, pre_cur,
                                             0x7fffffff, smem_u32(sbias));
                     pre_cur = pre_nxt;
                 } else {
