@@ -169,13 +169,20 @@ class FastPitch2Wave(nn.Module):
             wav = self.denoiser.denoise_batch(wav, dec_lens * self.vocoder.hop, denoise)
         lens = dec_lens.tolist()
         hop = self.vocoder.hop
+        order = inverse.tolist()
         if to_cpu:
-            host = torch.empty(wav.shape, dtype=wav.dtype, pin_memory=True)
+            # one D2H copy of the padded batch into a cached pinned staging buffer (allocating pinned memory per call
+            # costs more than the copy), then independent CPU tensors like the reference's `wav[0].cpu()`
+            n = wav.numel()
+            if getattr(self, '_pinned', None) is None or self._pinned.numel() < n:
+                self._pinned = torch.empty(n, dtype=torch.float32, pin_memory=True)
+            host = self._pinned[:n].view(wav.shape)
             host.copy_(wav, non_blocking=True)
             torch.cuda.current_stream(wav.device).synchronize()
-            wav = host
-        order = inverse.tolist()
-        return ([wav[row, :lens[row] * hop] for row in order], [mel[row, :, :lens[row]] for row in order])
+            wavs = [host[row, :lens[row] * hop].clone() for row in order]
+        else:
+            wavs = [wav[row, :lens[row] * hop] for row in order]
+        return (wavs, [mel[row, :, :lens[row]] for row in order])
 
     @torch.inference_mode()
     def tts_single(self, text_buckw: str, speed: float = 1, speaker_id: int = 0, denoise: float = 0, vowelizer=None,
