@@ -166,6 +166,18 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
         : "memory");
 }
 
+// TMA store of one box from shared memory (bulk async-group completion: commit, then wait for the READ of the source
+// tile before it is overwritten; the global writes complete in the background)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+        ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // 1-D bulk copy delivered to the same CTA-relative offset (data and mbarrier) in every CTA of `cta_mask`
 __device__ __forceinline__ void bulk_load_1d_multicast(void* smem_dst, const void* gsrc, uint32_t bytes,
                                                        uint64_t* bar, uint16_t cta_mask) {

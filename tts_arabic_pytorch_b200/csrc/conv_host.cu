@@ -93,7 +93,7 @@ int conv_layer_create(ConvLayer& L, int cin_logical, int cin_stored, int n_total
         const size_t full = kSmemMax - 2048;
         const size_t half = kSmemMax / 2 - 2048;
         const int total_b = L.n_chunks * n_taps;
-        const size_t bar_bytes = 1024 + 1024 + 8192 + 2048 + 256;   // alignment slack, barriers, epilogue staging tiles, bias tile
+        const size_t bar_bytes = 1024 + 1024 + 1024 + 8192 + 2048 + 256;   // alignment slack, barriers, epilogue staging tiles, bias tile
         const size_t w_all = static_cast<size_t>(total_b) * btile;
         const int min_a = std::min(L.n_chunks, 2);
         const size_t third = kSmemMax / 3 - 2048;
@@ -127,7 +127,7 @@ int conv_layer_create(ConvLayer& L, int cin_logical, int cin_stored, int n_total
             TTSB_REQUIRE(as2 >= rpp * std::min(L.n_chunks, 2), "resident plan: panel ring too small for rpp");
             L.a_slots2 = as2;
             L.b_stages2 = 1;
-            L.smem_bytes2 = 1024 + as2 * panel + w_all + (2 * as2 + 2 + 5) * 8 + 16 + 8192 + 2048 + 256;
+            L.smem_bytes2 = 1024 + as2 * panel + w_all + (2 * as2 + 2 + 5) * 8 + 16 + 1024 + 8192 + 2048 + 256;
         } else {
             const int item = rpp * L.n_chunks;                 // panels of one work item
             const int min_b = std::min(L.occ2 >= 2 ? 3 : 4, total_b);
@@ -142,7 +142,7 @@ int conv_layer_create(ConvLayer& L, int cin_logical, int cin_stored, int n_total
             TTSB_REQUIRE(bs2 >= 2 && as2 >= rpp, "persistent tile does not fit in shared memory");
             L.a_slots2 = as2;
             L.b_stages2 = bs2;
-            L.smem_bytes2 = 1024 + as2 * panel + bs2 * btile + (2 * as2 + 2 * bs2 + 5) * 8 + 16 + 8192 + 2048 + 256;
+            L.smem_bytes2 = 1024 + as2 * panel + bs2 * btile + (2 * as2 + 2 * bs2 + 5) * 8 + 16 + 1024 + 8192 + 2048 + 256;
         }
     }
 

@@ -43,6 +43,7 @@ struct ConvTc2Args {
     int step[2];       // off(tap+1) - off(tap)
     int halo_lo;
     const __half* w;
+    int tma_out;       // bit 0 / 1 / 2: out_raw / out_act / mrf_buf leave through TMA stores (lean epilogue)
     int params_smem;   // general epilogue: [bias][ln_g][ln_b][head_w] of this N tile staged in shared memory (room permitting)
     int* err_flag;
     long long* timeline;   // debug (tools/timeline.py): 64 clock64() slots per CTA for the first 256 CTAs, or null
@@ -59,7 +60,9 @@ __device__ __forceinline__ void tl2_mark(const ConvTc2Args& a, int slot) {
 // kEpi: 0 = general epilogue, 1 = lean (vocoder hot subset), 2 = lean + MRF accumulate
 template <int kTmemCols, int kMinBlocks, int kEpi>
 __global__ void __launch_bounds__(192, kMinBlocks)
-conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ ConvTc2Args args) {
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ ConvTc2Args args,
+                const __grid_constant__ CUtensorMap tmap_raw, const __grid_constant__ CUtensorMap tmap_act,
+                const __grid_constant__ CUtensorMap tmap_mrf) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_u32 = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw_u32 & 1023u)) & 1023u);
@@ -80,7 +83,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     uint64_t* w_full = tmem_empty + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
     // 4 x 2 KB staging tiles for the epilogue warps' coalesced row I/O (epilogue.cuh)
-    uint8_t* smem_stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 127) & ~static_cast<uintptr_t>(127));
+    // 1 KB aligned: the staging tiles double as TMA-store sources with the 64-byte swizzle (address-bit XOR)
+    uint8_t* smem_stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 1023) & ~static_cast<uintptr_t>(1023));
     float* sbias = reinterpret_cast<float*>(smem_stage + 4 * 2048);   // [n_tile] this N tile's bias (lean epilogue: smem broadcast)
 
     const int warp = threadIdx.x >> 5;
@@ -321,7 +325,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     RowIO nio{stage, lane, min(32, max(0, args.T - nw0))};
                     lean_prefetch(args.epi, nio, static_cast<long>(nb) * args.T + nw0, n_base, nvalid, pre_nxt, nb);
                     run_epilogue_lean<kMrf, true, !(kMrf && kMinBlocks >= 2)>(args.epi, acc, b, t, n_base, args.n_tile, wait_acc, drained, stage, pre_cur,
-                                            0x7fffffff, smem_u32(sbias));
+                                            0x7fffffff, smem_u32(sbias), (args.tma_out & 1) ? &tmap_raw : nullptr,
+                                            (args.tma_out & 2) ? &tmap_act : nullptr, (args.tma_out & 4) ? &tmap_mrf : nullptr);
                     pre_cur = pre_nxt;
                 } else {
                     long long* dbg = (tl_on && args.timeline != nullptr && blockIdx.x < 256 && tl_i < 7)
@@ -335,6 +340,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             if (args.acc_bufs == 2) buf ^= 1;
         }
     }
+    if (warp >= 2 && args.tma_out != 0 && elect_one()) tma_store_wait_all0();   // smem must outlive the bulk stores
     tc_fence_before();
     __syncthreads();
     if (csize == 2) cluster_sync_all();   // no CTA may exit while its peer can still multicast into it
@@ -407,8 +413,12 @@ int num_sms() {
     return n;
 }
 
+struct OutMaps {
+    CUtensorMap raw, act, mrf;
+};
+
 template <int kCols, int kMinBlocks, int kEpi>
-static int launch_two_impl(const CUtensorMap& tm, const ConvTc2Args& a, int grid, size_t smem, cudaStream_t s) {
+static int launch_two_impl(const CUtensorMap& tm, const ConvTc2Args& a, int grid, size_t smem, cudaStream_t s, const OutMaps& om) {
     static bool configured = false;
     if (!configured) {
         TTSB_CHECK_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<kCols, kMinBlocks, kEpi>,
@@ -428,9 +438,9 @@ static int launch_two_impl(const CUtensorMap& tm, const ConvTc2Args& a, int grid
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        TTSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<kCols, kMinBlocks, kEpi>, tm, a));
+        TTSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<kCols, kMinBlocks, kEpi>, tm, a, om.raw, om.act, om.mrf));
     } else {
-        conv_tc2_kernel<kCols, kMinBlocks, kEpi><<<grid, 192, smem, s>>>(tm, a);
+        conv_tc2_kernel<kCols, kMinBlocks, kEpi><<<grid, 192, smem, s>>>(tm, a, om.raw, om.act, om.mrf);
     }
     count_launch();
     TTSB_CHECK_CUDA(cudaGetLastError());
@@ -442,10 +452,10 @@ static bool host_epi_is_lean(const EpiParams& e) {
            e.act_tanh == 0 && e.pre_ln_relu == 0;
 }
 template <int kCols, int kMinBlocks>
-static int launch_two(const CUtensorMap& tm, const ConvTc2Args& a, int grid, size_t smem, cudaStream_t s) {
-    if (!host_epi_is_lean(a.epi)) return launch_two_impl<kCols, kMinBlocks, 0>(tm, a, grid, smem, s);
-    if (a.epi.mrf_mode == MRF_NONE) return launch_two_impl<kCols, kMinBlocks, 1>(tm, a, grid, smem, s);
-    return launch_two_impl<kCols, kMinBlocks, 2>(tm, a, grid, smem, s);
+static int launch_two(const CUtensorMap& tm, const ConvTc2Args& a, int grid, size_t smem, cudaStream_t s, const OutMaps& om) {
+    if (!host_epi_is_lean(a.epi)) return launch_two_impl<kCols, kMinBlocks, 0>(tm, a, grid, smem, s, om);
+    if (a.epi.mrf_mode == MRF_NONE) return launch_two_impl<kCols, kMinBlocks, 1>(tm, a, grid, smem, s, om);
+    return launch_two_impl<kCols, kMinBlocks, 2>(tm, a, grid, smem, s, om);
 }
 
 int conv_forward_tc2(const ConvLayer& L, const ConvRuntime& rt, const __half* in, int ld_in, int B,
@@ -461,7 +471,7 @@ int conv_forward_tc2(const ConvLayer& L, const ConvRuntime& rt, const __half* in
 
     const CUtensorMap* tmp = nullptr;
     TTSB_PROPAGATE(get_act_tensor_map(in, ld_in, B, T, L.cin, L.chunk_k, L.rows_panel, &tmp));
-    const CUtensorMap& tm = *tmp;
+    const CUtensorMap tm = *tmp;      // by value: the cache may reallocate on the next lookup
 
     ConvTc2Args a;
     a.B = B; a.T = T;
@@ -488,6 +498,23 @@ int conv_forward_tc2(const ConvLayer& L, const ConvRuntime& rt, const __half* in
     a.w = L.w_packed; a.err_flag = rt.err_flag; a.epi = epi;
     a.timeline = rt.timeline;
 
+    // lean epilogue: outputs leave through TMA stores of 32-row x 32-column blocks (64-byte swizzle = the staging
+    // tiles' XOR pattern); the maps are the activation map function with a 32 x 32 box over [B][T][n_total]
+    OutMaps om;
+    om.raw = om.act = om.mrf = tm;
+    a.tma_out = 0;
+    static const int want_tma_out = getenv("TTSB_TMA_OUT") ? atoi(getenv("TTSB_TMA_OUT")) : 1;
+    if (want_tma_out && host_epi_is_lean(epi)) {
+        struct { __half* p; int ld; CUtensorMap* m; int bit; } outs[3] = {
+            {epi.out_raw, epi.ld_raw, &om.raw, 1}, {epi.out_act, epi.ld_act, &om.act, 2}, {epi.mrf_buf, L.n_total, &om.mrf, 4}};
+        for (auto& o : outs) {
+            if (o.p == nullptr || (reinterpret_cast<uintptr_t>(o.p) & 15) != 0 || o.ld % 8 != 0 || o.ld < L.n_total) continue;
+            const CUtensorMap* t = nullptr;
+            TTSB_PROPAGATE(get_act_tensor_map(o.p, o.ld, B, T, L.n_total, 32, 32, &t));
+            *o.m = *t;
+            a.tma_out |= o.bit;
+        }
+    }
     // general epilogue with LayerNorm: stage the per-column parameters in shared memory when the plan leaves room
     // (2 KB are always reserved for the lean epilogue's bias tile)
     a.params_smem = 0;
@@ -515,27 +542,27 @@ int conv_forward_tc2(const ConvLayer& L, const ConvRuntime& rt, const __half* in
     // the register cap follows the planned CTAs per SM (1: 255, 2: 168, 3: 112 registers per thread)
     if (L.occ2 >= 3) {
         switch (L.tmem_cols2) {
-            case 32: return launch_two<32, 3>(tm, a, ctas, smem_bytes, stream);
-            case 64: return launch_two<64, 3>(tm, a, ctas, smem_bytes, stream);
-            case 128: return launch_two<128, 3>(tm, a, ctas, smem_bytes, stream);
+            case 32: return launch_two<32, 3>(tm, a, ctas, smem_bytes, stream, om);
+            case 64: return launch_two<64, 3>(tm, a, ctas, smem_bytes, stream, om);
+            case 128: return launch_two<128, 3>(tm, a, ctas, smem_bytes, stream, om);
         }
         TTSB_REQUIRE(false, "occupancy 3 needs <= 128 TMEM columns");
     }
     if (L.occ2 == 2) {
         switch (L.tmem_cols2) {
-            case 32: return launch_two<32, 2>(tm, a, ctas, smem_bytes, stream);
-            case 64: return launch_two<64, 2>(tm, a, ctas, smem_bytes, stream);
-            case 128: return launch_two<128, 2>(tm, a, ctas, smem_bytes, stream);
-            case 256: return launch_two<256, 2>(tm, a, ctas, smem_bytes, stream);
+            case 32: return launch_two<32, 2>(tm, a, ctas, smem_bytes, stream, om);
+            case 64: return launch_two<64, 2>(tm, a, ctas, smem_bytes, stream, om);
+            case 128: return launch_two<128, 2>(tm, a, ctas, smem_bytes, stream, om);
+            case 256: return launch_two<256, 2>(tm, a, ctas, smem_bytes, stream, om);
         }
         TTSB_REQUIRE(false, "occupancy 2 needs <= 256 TMEM columns");
     }
     switch (L.tmem_cols2) {
-        case 32: return launch_two<32, 1>(tm, a, ctas, smem_bytes, stream);
-        case 64: return launch_two<64, 1>(tm, a, ctas, smem_bytes, stream);
-        case 128: return launch_two<128, 1>(tm, a, ctas, smem_bytes, stream);
-        case 256: return launch_two<256, 1>(tm, a, ctas, smem_bytes, stream);
-        case 512: return launch_two<512, 1>(tm, a, ctas, smem_bytes, stream);
+        case 32: return launch_two<32, 1>(tm, a, ctas, smem_bytes, stream, om);
+        case 64: return launch_two<64, 1>(tm, a, ctas, smem_bytes, stream, om);
+        case 128: return launch_two<128, 1>(tm, a, ctas, smem_bytes, stream, om);
+        case 256: return launch_two<256, 1>(tm, a, ctas, smem_bytes, stream, om);
+        case 512: return launch_two<512, 1>(tm, a, ctas, smem_bytes, stream, om);
     }
     TTSB_REQUIRE(false, "bad tmem_cols");
     return 1;

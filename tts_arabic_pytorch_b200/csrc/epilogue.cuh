@@ -112,6 +112,28 @@ struct RowIO {
     int lane;
     int rows_valid;     // rows of this warp inside [0, T): clamp(T - warp_row0, 0, 32)
 
+    // A TMA store may still be reading the tile: the lane that issued it (elect.sync = lowest lane) waits for the
+    // read to finish before anyone overwrites the tile. Cheap when nothing is pending.
+    __device__ __forceinline__ void release_tile() const {
+        if (elect_one()) tma_store_wait_read0();
+        __syncwarp();
+    }
+    // write this lane's own row (4 units) of a [32 x 32] block through ONE TMA store: the tile's XOR pattern is the
+    // 64-byte TMA swizzle, so the row-owner layout goes out as it is — no LDS / STG / address arithmetic per lane.
+    // (c_col, c_row, c_b) = tensor coordinates of the block; rows beyond the tensor are clipped by the TMA unit.
+    __device__ __forceinline__ void store_tma(const CUtensorMap* tm, int c_col, int c_row, int c_b, const Chunk32& own) const {
+        const uint32_t base = smem_u32(tile);
+        release_tile();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) sts128(base + wtile_off(lane, u), own.q[u]);
+        fence_proxy_async();
+        __syncwarp();
+        if (rows_valid > 0 && elect_one()) {
+            tma_store_3d(tm, tile, c_col, c_row, c_b);
+            tma_store_commit();
+        }
+    }
+
     // request a [32 x 32] block whose (row 0, col 0) element is at `blk` (row pitch ld elements)
     __device__ __forceinline__ void request(const __half* blk, long ld, bool on, Chunk32& c) const {
 #pragma unroll
@@ -122,9 +144,10 @@ struct RowIO {
         }
     }
     // turn a requested block into this lane's own row (4 units of 8 columns)
-    __device__ __forceinline__ void to_row(Chunk32& c) const {
+    __device__ __forceinline__ void to_row(Chunk32& c, bool tma_in_use = false) const {
         if (!tile) return;
         const uint32_t base = smem_u32(tile);
+        if (tma_in_use) release_tile();
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -136,7 +159,8 @@ struct RowIO {
         for (int u = 0; u < 4; ++u) c.q[u] = lds128(base + wtile_off(lane, u));
     }
     // write this lane's own row (4 units) of a [32 x 32] block
-    __device__ __forceinline__ void store(__half* blk, long ld, const Chunk32& own) const {
+    __device__ __forceinline__ void store(__half* blk, long ld, const Chunk32& own, bool tma_in_use = false) const {
+        if (tile && tma_in_use) release_tile();
         if (!tile) {
             if (lane < rows_valid) {
 #pragma unroll
@@ -380,7 +404,9 @@ template <bool kMrf, bool kSmemBias = false, bool kLookahead = true, class Acc, 
 __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc& acc, int b, int t, int n_base,
                                                   int n_tile, WaitFn wait_acc, DrainFn acc_drained, uint8_t* stage,
                                                   const LeanPrefetch<kMrf>& pre, int t_end = 0x7fffffff,
-                                                  uint32_t bias_saddr = 0) {
+                                                  uint32_t bias_saddr = 0, const CUtensorMap* tm_raw = nullptr,
+                                                  const CUtensorMap* tm_act = nullptr, const CUtensorMap* tm_mrf = nullptr) {
+    // tm_*: when non-null the matching output leaves through TMA stores of 32 x 32 blocks (RowIO::store_tma)
     // kSmemBias: bias_saddr is the shared-memory address of this N tile's bias floats (else e.bias through __ldg)
     // t_end: exclusive row limit of this tile's stores (conv_pair tiles own fewer than 128 rows)
     const int lane = threadIdx.x & 31;
@@ -414,8 +440,9 @@ __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc&
             io.request(res_blk + c0, e.ld_res, use_res, res_cur);
             if (kMrf) io.request(mrf_blk + c0, e.n_total, use_mrf, mrf_cur);
         }
-        if (use_res) io.to_row(res_cur);
-        if (kMrf && use_mrf) io.to_row(mrf_cur);
+        const bool tma_out = tm_raw != nullptr || tm_act != nullptr || tm_mrf != nullptr;
+        if (use_res) io.to_row(res_cur, tma_out);
+        if (kMrf && use_mrf) io.to_row(mrf_cur, tma_out);
         __syncwarp();
         acc.load(c0, v);
         if (!more) acc_drained();
@@ -446,10 +473,17 @@ __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc&
             }
         }
         if (mrf_store) {
-            io.store(mrf_blk + c0, e.n_total, o_raw);
+            if (tm_mrf) io.store_tma(tm_mrf, n_base + c0, warp_row0, b, o_raw);
+            else io.store(mrf_blk + c0, e.n_total, o_raw, tma_out);
         } else {
-            if (e.out_raw) io.store(e.out_raw + row0 * e.ld_raw + n_base + c0, e.ld_raw, o_raw);
-            if (want_act) io.store(e.out_act + row0 * e.ld_act + n_base + c0, e.ld_act, o_act);
+            if (e.out_raw) {
+                if (tm_raw) io.store_tma(tm_raw, n_base + c0, warp_row0, b, o_raw);
+                else io.store(e.out_raw + row0 * e.ld_raw + n_base + c0, e.ld_raw, o_raw, tma_out);
+            }
+            if (want_act) {
+                if (tm_act) io.store_tma(tm_act, n_base + c0, warp_row0, b, o_act);
+                else io.store(e.out_act + row0 * e.ld_act + n_base + c0, e.ld_act, o_act, tma_out);
+            }
         }
         if (kLookahead) {
             res_cur = res_nxt;
