@@ -20,8 +20,8 @@
 // mid epilogue turns acc1(i) into TT(i); both accumulators are double-buffered in TMEM (4*C columns).
 //
 // Warp roles (512 threads): 0 TMA producer (x panels, resident weights), 1 conv1 MMA issuer, 2 conv2 MMA issuer,
-// 3 W2 ring producer (streamed W2 only), 4-7 mid epilogue, 8-11 final epilogue (the lean epilogue of
-// epilogue.cuh), 12-15 lrelu transform.
+// 3 W2 ring producer (streamed W2 only), 4-7 lrelu transform + mid epilogue, 8-11 and 12-15 two final-epilogue groups
+// (the lean epilogue of epilogue.cuh) that take alternate items.
 #include <cstdlib>
 #include "conv.cuh"
 
@@ -44,6 +44,7 @@ struct ConvPairArgs {
     int tt_rows;      // TT panel rows per chunk (multiple of 8, >= 128 + 2*h2)
     int x_slots, tt_slots;
     int w2_resident, b_stages;
+    int xform_final;  // 1: the final-epilogue groups run the lrelu transform (4 items ahead; needs x_slots >= 6), 0: the mid group
     const __half* w1;
     const __half* w2;
     const float* bias1;
@@ -70,6 +71,25 @@ __device__ __forceinline__ uint32_t lrelu_h2(uint32_t u, __half2 slope2) {
 }
 
 // kTmemCols = 4 * C: 128 -> C = 32 (32-channel rows, 64 B swizzle, 2 K steps per tap), 256 / 512 -> C = 64 / 128
+// lrelu of one landed x slot, in place, by the 128 threads of one warp group (tid = 0..127); arrives on xl_full (count 4)
+__device__ __forceinline__ void pair_transform_slot(const ConvPairArgs& args, uint8_t* slot, int units, uint64_t* x_full,
+                                                    uint64_t* xl_full, uint32_t parity, int tid, int item) {
+    mbar_wait(x_full, parity, args.err_flag, 309);
+    if (tid == 0) tlp_mark(args, item, 1);
+    const __half2 slope2 = __float2half2_rn(args.slope);
+    const uint32_t base = smem_u32(slot);
+    for (int i = tid; i < ((args.debug & 1) ? 0 : units); i += 128) {
+        uint4 v = lds128(base + i * 16);
+        v.x = lrelu_h2(v.x, slope2); v.y = lrelu_h2(v.y, slope2);
+        v.z = lrelu_h2(v.z, slope2); v.w = lrelu_h2(v.w, slope2);
+        sts128(base + i * 16, v);
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (elect_one()) mbar_arrive(xl_full);
+    if (tid == 0) tlp_mark(args, item, 2);
+}
+
 template <int kTmemCols, int kEpi>
 __global__ void __launch_bounds__(kPairThreads, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ ConvPairArgs args) {
@@ -107,7 +127,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     uint64_t* w_full = acc2_empty + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
     uint8_t* smem_stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 127) & ~static_cast<uintptr_t>(127));
-    float* sbias1 = reinterpret_cast<float*>(smem_stage + 4 * 2048);   // [C] conv1 bias, [C] conv2 bias: the epilogues read
+    float* sbias1 = reinterpret_cast<float*>(smem_stage + 8 * 2048);   // [C] conv1 bias, [C] conv2 bias: the epilogues read
     float* sbias2 = sbias1 + args.C;                                   // them as shared-memory broadcasts, not through L1/L2
 
     const int warp = threadIdx.x >> 5;
@@ -276,29 +296,6 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 }
             }
         }
-    } else if (warp >= 12) {
-        // ---------------- lrelu transform, in place on the landed x panel (4 warps) ----------------
-        const int tid = threadIdx.x - 12 * 32;
-        const __half2 slope2 = __float2half2_rn(args.slope);
-        const int units = xslot_bytes >> 4;
-        int sx = 0, it = 0;
-        uint32_t px = 0;
-        for (int idx = blockIdx.x; idx < args.n_work; idx += grid, ++it) {
-            mbar_wait(&x_full[sx], px, args.err_flag, 309);
-            if (tid == 0) tlp_mark(args, it, 1);
-            const uint32_t base = smem_u32(smem_x + sx * xslot_bytes);
-            for (int i = tid; i < ((args.debug & 1) ? 0 : units); i += kPairXformWarps * 32) {
-                uint4 v = lds128(base + i * 16);
-                v.x = lrelu_h2(v.x, slope2); v.y = lrelu_h2(v.y, slope2);
-                v.z = lrelu_h2(v.z, slope2); v.w = lrelu_h2(v.w, slope2);
-                sts128(base + i * 16, v);
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (elect_one()) mbar_arrive(&xl_full[sx]);
-            if (tid == 0) tlp_mark(args, it, 2);
-            if (++sx == args.x_slots) { sx = 0; px ^= 1; }
-        }
     } else if (warp < 8) {
         // ---------------- mid epilogue: acc1 -> lrelu(acc + b1) * rowmask -> TT panel (UMMA layout) ----------------
         const int q = warp & 3;
@@ -311,6 +308,22 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         int it = 0;
         const uint32_t sb1 = smem_u32(sbias1);
         const bool use_sbias = (args.debug & 16) == 0;
+        // This group also runs the lrelu transform of the landed x panels (in place), `la` items ahead of its own
+        // accumulator work: the four warps the transform used to own are the second final-epilogue group now — the
+        // final epilogue (~4.5 k cycles per item) was the pipeline's slowest stage, this group has the slack.
+        const int tid = threadIdx.x - 4 * 32;
+        const int units = xslot_bytes >> 4;
+        int sxt = 0;
+        uint32_t pxt = 0;
+        auto transform = [&](int j) {
+            pair_transform_slot(args, smem_x + sxt * xslot_bytes, units, &x_full[sxt], &xl_full[sxt], pxt, tid, j);
+            if (++sxt == args.x_slots) { sxt = 0; pxt ^= 1; }
+        };
+        int n_items = 0;
+        for (int idx = blockIdx.x; idx < args.n_work; idx += grid) ++n_items;
+        // x(it + la) is issued once conv1(it + la - x_slots) has completed; la = 0: the final groups transform
+        const int la = args.xform_final ? 0 : min(2, args.x_slots - 1);
+        for (int j = 0; j < la && j < n_items; ++j) transform(j);
         for (int idx = blockIdx.x; idx < args.n_work; idx += grid, ++it) {
             const int b = idx / args.tiles_t;
             const int t0 = (idx - b * args.tiles_t) * args.m_out;
@@ -355,31 +368,50 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             if (m == 0) tlp_mark(args, it, 9);
             b1 ^= 1;
             if (args.tt_slots == 2) st ^= 1;
+            if (la > 0 && it + la < n_items) transform(it + la);
         }
     } else {
         // ---------------- final epilogue: acc2 + b2 + x -> mask -> outputs (lean epilogue) ----------------
+        // two groups of four warps: group g takes the CTA's items g, g + 2, ... = accumulator buffer g
+        const int g = (warp - 8) >> 2;
         const int q = warp & 3;
         constexpr bool kMrf = kEpi == 2;
-        uint8_t* stage = smem_stage + q * 2048;
-        int b2 = 0;
-        uint32_t pf = 0;
+        uint8_t* stage = smem_stage + (warp - 8) * 2048;
+        const int b2 = g;
+        uint32_t par = 0;
         LeanPrefetch<kMrf> pre_cur, pre_nxt;
-        if (blockIdx.x < args.n_work) {
-            const int b0 = blockIdx.x / args.tiles_t;
-            const int t00 = (blockIdx.x - b0 * args.tiles_t) * args.m_out;
+        const int idx_first = blockIdx.x + g * grid;
+        if (idx_first < args.n_work) {
+            const int b0 = idx_first / args.tiles_t;
+            const int t00 = (idx_first - b0 * args.tiles_t) * args.m_out;
             const int w0 = t00 + q * 32;
             RowIO io{stage, lane, min(32, max(0, min(args.T, t00 + args.m_out) - w0))};
             lean_prefetch(args.epi, io, static_cast<long>(b0) * args.T + w0, 0, true, pre_cur, b0);
         }
-        int it = 0;
         const bool tl_on = q == 0 && lane == 0;
-        for (int idx = blockIdx.x; idx < args.n_work; idx += grid, ++it) {
+        // With a deep x ring the transform lives here, four items ahead of this group's own item (same parity, so each
+        // group transforms exactly the panels whose results it will finish): two groups x 3.1 k cycles per item leave
+        // more slack than the mid group has. conv1(j) then waits for final(j - 4), four items behind it anyway.
+        int n_items = 0;
+        for (int idx = blockIdx.x; idx < args.n_work; idx += grid) ++n_items;
+        const int tid = threadIdx.x - (8 + 4 * g) * 32;
+        const int units = xslot_bytes >> 4;
+        auto transform = [&](int j) {
+            const int sx = j % args.x_slots;
+            pair_transform_slot(args, smem_x + sx * xslot_bytes, units, &x_full[sx], &xl_full[sx],
+                                static_cast<uint32_t>(j / args.x_slots) & 1u, tid, j);
+        };
+        if (args.xform_final) {
+            if (g < n_items) transform(g);
+            if (g + 2 < n_items) transform(g + 2);
+        }
+        int it = g;
+        for (int idx = idx_first; idx < args.n_work; idx += 2 * grid, it += 2) {
             const int b = idx / args.tiles_t;
             const int t0 = (idx - b * args.tiles_t) * args.m_out;
             const int t = t0 + q * 32 + lane;
             if (tl_on) tlp_mark(args, it, 10);
             TmemAcc acc{tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc2_col + b2 * C};
-            const uint32_t par = (pf >> b2) & 1u;
             auto wait_acc = [&] {
                 mbar_wait(&acc2_full[b2], par, args.err_flag, 312);
                 tc_fence_after();
@@ -390,7 +422,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 __syncwarp();
                 if (elect_one()) mbar_arrive(&acc2_empty[b2]);
             };
-            const int nidx = idx + grid;
+            const int nidx = idx + 2 * grid;
             const bool nvalid = nidx < args.n_work;
             const int nb = nvalid ? nidx / args.tiles_t : 0;
             const int nt0 = nvalid ? (nidx - nb * args.tiles_t) * args.m_out : 0;
@@ -409,8 +441,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             }
             pre_cur = pre_nxt;
             if (tl_on) tlp_mark(args, it, 12);
-            pf ^= 1u << b2;
-            b2 ^= 1;
+            par ^= 1;
+            if (args.xform_final && it + 4 < n_items) transform(it + 4);
         }
     }
     tc_fence_before();
@@ -422,7 +454,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 // host
 // ------------------------------------------------------------------------------------------------
 static const size_t kPairSmemMax = 232448;
-static const size_t kPairFixed = 1024 /*alignment*/ + 1024 /*barriers + tmem slot*/ + 8192 /*staging*/ + 512 /*biases*/ + 256;
+static const size_t kPairFixed = 1024 /*alignment*/ + 1024 /*barriers + tmem slot*/ + 16384 /*staging: 8 warps*/ + 512 /*biases*/ + 256;
 
 ConvPairPlan conv_pair_plan(const ConvLayer& L1, const ConvLayer& L2) {
     ConvPairPlan p;
@@ -508,6 +540,9 @@ int conv_pair_forward(const ConvLayer& L1, const ConvLayer& L2, const ConvPairPl
     a.rows_panel = plan.rows_panel; a.tt_rows = plan.tt_rows;
     a.x_slots = plan.x_slots; a.tt_slots = plan.tt_slots;
     a.w2_resident = plan.w2_resident; a.b_stages = plan.b_stages;
+    // measured neutral against the mid-group transform (profiles/r01_s48_pair_two_final_groups.txt): off unless asked for
+    static const int xform_final = getenv("TTSB_PAIR_XFORM_FINAL") ? atoi(getenv("TTSB_PAIR_XFORM_FINAL")) : 0;
+    a.xform_final = (xform_final && plan.x_slots >= 6) ? 1 : 0;
     a.w1 = L1.w_packed; a.w2 = L2.w_packed;
     a.bias1 = L1.bias;
     a.slope = slope;
