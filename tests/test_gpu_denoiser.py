@@ -71,3 +71,30 @@ def test_forward_keeps_the_reference_call_shape(denoiser):
     assert float((y0 - audio).abs().max()) < 1e-5
     with pytest.raises(RuntimeError, match='no CPU path'):
         denoiser(audio.cpu(), 0.005)
+
+
+def test_cuda_denoiser_matches_reference_golden(denoiser, golden_dir):
+    """The fixture holds outputs of the REAL reference Denoiser (oracle/make_golden_denoiser.py): same bias spectrum,
+    same waveforms in, the CUDA kernels must reproduce its waveforms; the two utterances go through as one padded
+    batch with their own lengths."""
+    import os
+    g = np.load(os.path.join(golden_dir, 'denoiser_small.npz'))
+    dev = torch.device('cuda:0')
+    denoiser._ensure_bias(dev)
+    own_bias = denoiser.bias_spec.detach().cpu().numpy()
+    # the bias spectrum computed from OUR generator's zero-mel response against the reference's (fp16 vocoder path)
+    assert np.abs(own_bias - g['bias_spec']).max() < 2e-2 * max(1.0, float(np.abs(g['bias_spec']).max()))
+    saved = denoiser.bias_spec
+    try:
+        denoiser.bias_spec = torch.from_numpy(g['bias_spec']).to(dev)        # isolate the transform kernels
+        n0, n1 = g['audio0'].shape[1], g['audio1'].shape[1]
+        wav = torch.zeros(2, n0)
+        wav[0] = torch.from_numpy(g['audio0'][0])
+        wav[1, :n1] = torch.from_numpy(g['audio1'][0])
+        for s in (0.005, 0.1):
+            out = denoiser.denoise_batch(wav.to(dev), torch.tensor([n0, n1]), s).cpu().numpy()
+            assert np.abs(out[0] - g['out0_s%g' % s][0]).max() < DENOISE_ABS_TOL
+            assert np.abs(out[1, :n1] - g['out1_s%g' % s][0]).max() < DENOISE_ABS_TOL
+            assert np.abs(out[1, n1:]).max() == 0.0
+    finally:
+        denoiser.bias_spec = saved

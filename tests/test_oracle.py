@@ -124,3 +124,27 @@ def test_tacotron2_oracle_matches_reference_with_injected_masks(golden_dir):
     assert np.abs(align.numpy() - g['alignments']).max() < TOL
     # attention never looks at padded tokens
     assert float(align[1, :, 10:].abs().max()) == 0.0 and float(align[2, :, 5:].abs().max()) == 0.0
+
+
+def test_denoiser_oracle_matches_reference_fixture(golden_dir, hifigan_weights):
+    """oracle/denoiser_oracle.py against outputs of the real reference Denoiser (torchaudio Spectrogram /
+    InverseSpectrogram, vocoder/hifigan/denoiser.py:29-72) minted by oracle/make_golden_denoiser.py."""
+    import numpy as np
+    import torch
+    from oracle import denoiser_oracle as dno
+    from oracle import hifigan_oracle as hgo
+    from tts_arabic_pytorch_b200.utils import synth
+    g = np.load(os.path.join(golden_dir, 'denoiser_small.npz'))
+    # bias spectrum: zero-mel response of the (oracle) generator, first STFT frame (denoiser.py:51-64)
+    zero_audio = hgo.generator_forward(hifigan_weights, synth.HIFIGAN_CONFIG, torch.zeros(1, 80, 88))
+    bias = dno.bias_spectrum(zero_audio)
+    assert bias.shape == (1, 513, 1)
+    assert np.abs(bias.numpy() - g['bias_spec']).max() < 2e-4 * max(1.0, float(np.abs(g['bias_spec']).max()))
+    ref_bias = torch.from_numpy(g['bias_spec'])
+    for name in ('0', '1'):
+        audio = torch.from_numpy(g['audio' + name])
+        for s in (0.005, 0.1):
+            out = dno.denoise(audio, ref_bias, s).numpy()
+            ref = g['out%s_s%g' % (name, s)]
+            assert out.shape == ref.shape
+            assert np.abs(out - ref).max() < 1e-5
