@@ -307,7 +307,6 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const uint32_t phase = row_bytes == 128 ? (m & 7) : ((m >> 1) & 3);
         int it = 0;
         const uint32_t sb1 = smem_u32(sbias1);
-        const bool use_sbias = (args.debug & 16) == 0;
         // This group also runs the lrelu transform of the landed x panels (in place), `la` items ahead of its own
         // accumulator work: the four warps the transform used to own are the second final-epilogue group now — the
         // final epilogue (~4.5 k cycles per item) was the pipeline's slowest stage, this group has the slack.
@@ -348,8 +347,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     float bs[8], a[8];
-                    if (use_sbias) bias8s(sb1 + (c0 + g * 8) * 4, bs);
-                    else bias8(args.bias1, c0 + g * 8, bs);
+                    bias8s(sb1 + (c0 + g * 8) * 4, bs);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float y = v[g * 8 + j] + bs[j];
