@@ -69,3 +69,21 @@ def test_collate_sorts_pads_and_inverts():
     for i, src in enumerate(batch):
         row = padded[inverse[i]]
         assert row[:src.numel()].tolist() == src.tolist() and int(row[src.numel():].sum()) == 0
+
+
+def test_word_cache_is_transparent():
+    """word phonetisation is memoised: results must not depend on cache state and a caller
+    editing a returned list must not poison later calls."""
+    from tts_arabic_pytorch_b200 import text
+    from tts_arabic_pytorch_b200.text import phonetiser
+    line = ">als~alAmu Ealaykum yA Sadiyqiy , >als~alAmu Ealaykum"
+    phonetiser._word_to_phones_cached.cache_clear()
+    cold = text.buckwalter_to_tokens(line)
+    warm = text.buckwalter_to_tokens(line)
+    assert cold == warm
+    ph = phonetiser.word_to_phones(">als~alAmu")
+    assert isinstance(ph, list)
+    ph.append('XX')
+    assert phonetiser.word_to_phones(">als~alAmu") == ph[:-1]
+    assert text.buckwalter_to_tokens(line) == cold
+    assert phonetiser._word_to_phones_cached.cache_info().hits > 0

@@ -9,6 +9,7 @@ _STRESSED = {'aa': ('aa', 'AA'), 'uu': ('uu0', 'uu1', 'UU0', 'UU1'), 'ii': ('ii0
 vowel_map = {variant: plain for plain, variants in _STRESSED.items() for variant in variants}
 vowels = list(vowel_map)
 phon_to_id_ = {phon: i for i, phon in enumerate(symbols)}
+_TOKEN_MEMO = {}
 
 
 def tokens_to_ids(phonemes, phon_to_id=None):
@@ -34,10 +35,14 @@ def phonemes_to_tokens(phonemes: str, append_space=True):
     toks = phonemes.replace('sil', '').replace('+', SEPARATOR_TOKEN).split()
     out = []
     for t in toks:
-        if len(t) == 2 and t not in vowel_map and t[0] == t[1]:
-            out += [t[0], DOUBLING_TOKEN]
-        else:
-            out.append(vowel_map.get(t, t))
+        m = _TOKEN_MEMO.get(t)
+        if m is None:       # the per-phoneme rule, evaluated once per distinct phoneme string
+            if len(t) == 2 and t not in vowel_map and t[0] == t[1]:
+                m = (t[0], DOUBLING_TOKEN)
+            else:
+                m = (vowel_map.get(t, t),)
+            _TOKEN_MEMO[t] = m
+        out.extend(m)
     if append_space:
         out.append(SEPARATOR_TOKEN)
     out.append(EOS_TOKEN)

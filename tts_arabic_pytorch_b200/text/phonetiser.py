@@ -7,6 +7,7 @@ pronunciation variants of a word and then keeps variant 0; this implementation w
 and emits that variant directly. `tests/test_text.py` checks it token-for-token against fixtures
 produced by the reference on its own corpus plus fuzzed strings.
 """
+import functools
 import re
 
 # ---- script conversion -----------------------------------------------------------------------
@@ -23,12 +24,16 @@ del _AR2BW[chr(0x0640)]     # tatweel is stripped later, not transliterated
 _BW2AR = {v: k for k, v in _AR2BW.items()}
 
 
+_AR2BW_TABLE = {ord(k): v for k, v in _AR2BW.items()}
+_BW2AR_TABLE = {ord(k): v for k, v in _BW2AR.items()}
+
+
 def arabic_to_buckwalter(s):
-    return ''.join(_AR2BW.get(c, c) for c in s)
+    return s.translate(_AR2BW_TABLE)
 
 
 def buckwalter_to_arabic(s):
-    return ''.join(_BW2AR.get(c, c) for c in s)
+    return s.translate(_BW2AR_TABLE)
 
 
 # ---- letter classes ----------------------------------------------------------------------------
@@ -227,11 +232,20 @@ def _tidy(phones):
     return phones
 
 
-def word_to_phones(word):
+@functools.lru_cache(maxsize=1 << 16)
+def _word_to_phones_cached(word):
+    """The phonetisation of a word depends on the word alone (the reference's process_word takes nothing else), and
+    running text repeats its words: once the GPU path synthesises ~10^4 x real time the rule walk is what a text batch
+    waits for. Tuples, so cached results cannot be edited by a caller."""
     if word in PUNCT:
         return word
     fixed = _irregular(word)
-    return _tidy(list(fixed) if fixed is not None else _walk(word))
+    return tuple(_tidy(list(fixed) if fixed is not None else _walk(word)))
+
+
+def word_to_phones(word):
+    ph = _word_to_phones_cached(word)
+    return ph if isinstance(ph, str) else list(ph)
 
 
 def utterance_to_phoneme_string(utterance):
@@ -240,7 +254,7 @@ def utterance_to_phoneme_string(utterance):
         if word in ('-', 'sil'):
             groups.append(['sil'])
             continue
-        ph = word_to_phones(word)
+        ph = _word_to_phones_cached(word)
         if isinstance(ph, str) and groups:       # punctuation attaches to the previous word
             groups[-1] = list(groups[-1]) + [ph]
         else:
