@@ -171,15 +171,15 @@ class FastPitch2Wave(nn.Module):
         hop = self.vocoder.hop
         order = inverse.tolist()
         if to_cpu:
-            # one D2H copy of the padded batch into a cached pinned staging buffer (allocating pinned memory per call
-            # costs more than the copy), then independent CPU tensors like the reference's `wav[0].cpu()`
-            n = wav.numel()
-            if getattr(self, '_pinned', None) is None or self._pinned.numel() < n:
-                self._pinned = torch.empty(n, dtype=torch.float32, pin_memory=True)
-            host = self._pinned[:n].view(wav.shape)
+            # one D2H copy of the padded batch into pinned memory; the per-utterance results are views of it. A fresh
+            # pinned tensor per call keeps earlier results valid (the reference returns independent `wav[0].cpu()`
+            # tensors) and costs no allocation in steady state: torch's caching host allocator recycles the blocks of
+            # results the caller has dropped. (A reused staging buffer + per-utterance clones measured 40 ms of host
+            # copies per 256-utterance batch, a quarter of the GPU step.)
+            host = torch.empty(wav.shape, dtype=wav.dtype, pin_memory=True)
             host.copy_(wav, non_blocking=True)
             torch.cuda.current_stream(wav.device).synchronize()
-            wavs = [host[row, :lens[row] * hop].clone() for row in order]
+            wavs = [host[row, :lens[row] * hop] for row in order]
         else:
             wavs = [wav[row, :lens[row] * hop] for row in order]
         return (wavs, [mel[row, :, :lens[row]] for row in order])
