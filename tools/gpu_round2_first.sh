@@ -1,0 +1,21 @@
+#!/bin/bash
+# First GPU call of the next round ("Working hypothesis for the C >= 128 layers"):
+#   1. today's kernels under the occupancy / rows-per-pass knobs (last measured before the epilogue fixes, profiles/r01_s23)
+#   2. the rotated weight-tile order, if tools/experiments/rotate_taps_conv_tc2.patch has been applied and the
+#      library rebuilt HERE before the call (TTSB_ROTATE_TAPS is ignored by an unpatched build)
+# ~3 GPU-minutes. Output: gpurun_out/round2_first.log
+set -u
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+exec > >(tee gpurun_out/round2_first.log) 2>&1
+run() { echo "=== $1"; shift; env "$@" timeout 300 python tools/bench_conv.py --batch 32 --only "$ONLY" --iters 7; }
+for ONLY in s1_128 s0_256; do
+    run "default $ONLY" TTSB_NOP=1
+    run "rotate $ONLY" TTSB_ROTATE_TAPS=1
+    run "occ1 rpp2 $ONLY" TTSB_OCC2=1 TTSB_RPP=2
+    run "occ1 rpp2 rotate $ONLY" TTSB_OCC2=1 TTSB_RPP=2 TTSB_ROTATE_TAPS=1
+    run "occ1 rpp1 $ONLY" TTSB_OCC2=1 TTSB_RPP=1
+done
+echo "=== vocoder parity with the rotated order (golden + oracle + SIMT cross-check)"
+TTSB_ROTATE_TAPS=1 timeout 600 python -m pytest tests/test_gpu_models.py -x -q -m gpu -k "hifigan or tcgen05" 2>&1 | tail -3
+echo "=== done"
