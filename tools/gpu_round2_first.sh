@@ -16,6 +16,10 @@ for ONLY in s1_128 s0_256; do
     run "occ1 rpp2 rotate $ONLY" TTSB_OCC2=1 TTSB_RPP=2 TTSB_ROTATE_TAPS=1
     run "occ1 rpp1 $ONLY" TTSB_OCC2=1 TTSB_RPP=1
 done
+# mma[gotTMEM gotA issued]: gotA - gotTMEM = wait for the A panel; (issued - gotA) / (n_chunks x n_taps) = weight-ring period
+echo "=== in-kernel timelines of the k=11 layers"
+timeout 120 python tools/timeline.py s1_128_k11_d5 32 | head -40
+timeout 120 python tools/timeline.py s0_256_k11_d5 32 | head -40
 echo "=== vocoder parity with the rotated order (golden + oracle + SIMT cross-check)"
 TTSB_ROTATE_TAPS=1 timeout 600 python -m pytest tests/test_gpu_models.py -x -q -m gpu -k "hifigan or tcgen05" 2>&1 | tail -3
 echo "=== done"
