@@ -1,5 +1,5 @@
 #!/bin/bash
-# First GPU call of the next round ("Working hypothesis for the C >= 128 layers"):
+# First GPU call of the next round ("What bounds the C >= 128 layers, and the next experiments"):
 #   1. today's kernels under the occupancy / rows-per-pass knobs (last measured before the epilogue fixes, profiles/r01_s23)
 #   2. the rotated weight-tile order / fast issue path, if tools/experiments/{fast_issue,rotate_taps}_conv_tc2.patch were applied and the
 #      library rebuilt HERE before the call (TTSB_ROTATE_TAPS is ignored by an unpatched build)
