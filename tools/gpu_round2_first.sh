@@ -20,6 +20,11 @@ done
 echo "=== in-kernel timelines of the k=11 layers"
 timeout 120 python tools/timeline.py s1_128_k11_d5 32 | head -40
 timeout 120 python tools/timeline.py s0_256_k11_d5 32 | head -40
+# conv_pair: k >= 7 items take ~2 x the summed MMA time although its issue loops are lean; find the stage that is late
+echo "=== conv_pair timelines, k = 11 / 7"
+timeout 120 python tools/timeline_pair.py 64 11 5 | head -30
+timeout 120 python tools/timeline_pair.py 64 7 3 | head -30
+timeout 120 python tools/timeline_pair.py 32 11 5 | head -30
 echo "=== vocoder parity with the rotated order (golden + oracle + SIMT cross-check)"
 TTSB_ROTATE_TAPS=1 timeout 600 python -m pytest tests/test_gpu_models.py -x -q -m gpu -k "hifigan or tcgen05" 2>&1 | tail -3
 echo "=== done"
