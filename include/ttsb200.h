@@ -206,6 +206,10 @@ void ttsb_convpair_destroy(ttsb_convpair_t* h);
 int ttsb_convpair_plan(const ttsb_convpair_t* h, int* out8);
 int ttsb_convpair_forward(ttsb_convpair_t* h, const void* d_x, int B, int T, const int32_t* d_lens, float slope,
                           void* d_out, void* stream);
+/* Same step on ACTIVATED tensors, the form the generator keeps in HBM: d_lx = lrelu(x, slope), d_lout = lrelu(out, slope)
+ * (the residual add inverts the activation; csrc/hifigan.cu). */
+int ttsb_convpair_forward_act(ttsb_convpair_t* h, const void* d_lx, int B, int T, const int32_t* d_lens, float slope,
+                              void* d_lout, void* stream);
 
 #ifdef __cplusplus
 }

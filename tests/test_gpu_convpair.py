@@ -47,7 +47,9 @@ def _make(C, k, dil, seed):
     return lib, h, list(plan), (w1, b1, w2, b2), g
 
 
-def _run_case(C, k, dil, T, lens, seed=0):
+def _run_case(C, k, dil, T, lens, seed=0, act=False):
+    """act=True: the generator's production form — tensors stored ACTIVATED (lrelu(x) in, lrelu(out) out), the
+    residual add inverts the activation (ttsb_convpair_forward_act)."""
     from tts_arabic_pytorch_b200 import _lib
     torch.backends.cudnn.allow_tf32 = False
     dev = _dev()
@@ -61,9 +63,17 @@ def _run_case(C, k, dil, T, lens, seed=0):
         xd = x.to(dev)
         ld = torch.tensor(lens, dtype=torch.int32, device=dev)
         out = torch.full((B, T, C), float('nan'), dtype=torch.float16, device=dev)
-        _lib.check(lib.ttsb_convpair_forward(h, _lib.ptr(xd), B, T, _lib.ptr(ld), 0.1, _lib.ptr(out), None))
+        if act:
+            # operand of the kernel: fp16(lrelu(x)); its exact inverse is the x the reference sees
+            lxd = torch.where(xd > 0, xd.float(), xd.float() * 0.1).half()
+            xd = torch.where(lxd > 0, lxd.float(), lxd.float() * 10.0)        # fp32, exactly what the epilogue recovers
+            _lib.check(lib.ttsb_convpair_forward_act(h, _lib.ptr(lxd), B, T, _lib.ptr(ld), 0.1, _lib.ptr(out), None))
+        else:
+            _lib.check(lib.ttsb_convpair_forward(h, _lib.ptr(xd), B, T, _lib.ptr(ld), 0.1, _lib.ptr(out), None))
         torch.cuda.synchronize()
         ref = _reference(xd, ld, w1.to(dev), b1.to(dev), w2.to(dev), b2.to(dev), k, dil, 0.1)
+        if act:
+            ref = torch.where(ref > 0, ref, ref * 0.1)
         o = out.float()
         assert not torch.isnan(o).any()
         scale = max(1.0, float(ref.abs().max()))
@@ -86,6 +96,13 @@ def test_pair_matches_torch_on_ragged_batch(C, k, dil):
     _run_case(C, k, dil, 4000, [4000, 3629, 129, 4000, 2500, 3999])
 
 
+@pytest.mark.parametrize('C', [32, 64])
+@pytest.mark.parametrize('k', [3, 7, 11])
+@pytest.mark.parametrize('dil', [1, 3, 5])
+def test_pair_on_activated_tensors_matches_torch(C, k, dil):
+    _run_case(C, k, dil, 4000, [4000, 3629, 129, 4000, 2500, 3999], seed=1, act=True)
+
+
 @pytest.mark.parametrize('C,k,dil', [(32, 11, 5), (64, 3, 1), (64, 11, 5)])
 def test_pair_edge_shapes(C, k, dil):
     m_out = 128 - (k - 1)
@@ -93,6 +110,8 @@ def test_pair_edge_shapes(C, k, dil):
     _run_case(C, k, dil, m_out, [m_out, m_out - 1])            # exactly one tile
     _run_case(C, k, dil, m_out + 1, [m_out + 1, 1])            # one row spills into a second tile
     _run_case(C, k, dil, 40 * m_out, [40 * m_out] * 8 + [17])  # persistent CTAs wrap (321 items over 148 CTAs)
+    _run_case(C, k, dil, m_out + 1, [m_out + 1, 1], act=True)
+    _run_case(C, k, dil, 40 * m_out, [40 * m_out] * 8 + [17], act=True)
 
 
 def test_pair_plan_reports_fallback_for_wide_layers():

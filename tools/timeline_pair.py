@@ -15,6 +15,7 @@ def main():
     import torch
     from tts_arabic_pytorch_b200 import _lib
     lib = _lib.load()
+    FWD = lib.ttsb_convpair_forward_act if os.environ.get('TTSB_PROBE_ACT', '1') == '1' else lib.ttsb_convpair_forward   # timing only
     C, k, dil = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
     B = int(sys.argv[4]) if len(sys.argv) > 4 else 16
     rpf = {64: 128, 32: 256}.get(C, 64)
@@ -32,11 +33,11 @@ def main():
     x = (torch.randn(B, T, C, generator=g) * 0.5).half().to(dev)
     out = torch.empty_like(x)
     for _ in range(2):
-        _lib.check(lib.ttsb_convpair_forward(h, _lib.ptr(x), B, T, None, 0.1, _lib.ptr(out), None))
+        _lib.check(FWD(h, _lib.ptr(x), B, T, None, 0.1, _lib.ptr(out), None))
     torch.cuda.synchronize()
     tl = torch.zeros(256 * 128, dtype=torch.int64, device=dev)
     lib.ttsb_debug_set_timeline(_lib.ptr(tl))
-    _lib.check(lib.ttsb_convpair_forward(h, _lib.ptr(x), B, T, None, 0.1, _lib.ptr(out), None))
+    _lib.check(FWD(h, _lib.ptr(x), B, T, None, 0.1, _lib.ptr(out), None))
     torch.cuda.synchronize()
     lib.ttsb_debug_set_timeline(None)
     t = tl.cpu().view(256, 128)

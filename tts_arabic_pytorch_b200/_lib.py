@@ -88,6 +88,7 @@ _SIGNATURES = {
     'ttsb_convpair_destroy': (None, [c_void_p]),
     'ttsb_convpair_plan': (c_int, [c_void_p, ctypes.POINTER(c_int)]),
     'ttsb_convpair_forward': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p]),
+    'ttsb_convpair_forward_act': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p]),
 }
 EXPORTS = tuple(sorted(_SIGNATURES))
 

@@ -9,6 +9,8 @@
 #include <cuda.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <exception>
+#include <memory>
 #include <string>
 
 namespace ttsb {
@@ -44,9 +46,55 @@ const char* get_last_error();
         if (_s != 0) return _s;                                                            \
     } while (0)
 
+// No C++ exception (std::bad_alloc, std::string growth in the macros above) may cross the extern "C" boundary into ctypes:
+// every int-returning entry point runs its body through this.
+template <class F>
+static inline int guarded_call(F&& f) {
+    try {
+        return f();
+    } catch (const std::exception& e) {
+        ::ttsb::set_last_error(std::string("C++ exception: ") + e.what());
+        return 3;
+    } catch (...) {
+        ::ttsb::set_last_error("unknown C++ exception");
+        return 3;
+    }
+}
+
 // launch accounting for bench.py's `gpu_launches` (ttsb_launch_count in the C ABI)
 void count_launch(int n = 1);
 long long launch_count();
+
+// Per-device process state. Every ttsb_*_create() takes a device ordinal, so nothing that belongs to a device (function
+// attributes, the SM count, the error flag, scratch buffers) may be cached once per process.
+constexpr int kMaxDevices = 64;
+static inline int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev < 0 ? 0 : (dev >= kMaxDevices ? kMaxDevices - 1 : dev);
+}
+struct PerDeviceOnce {
+    bool done[kMaxDevices] = {};
+    bool& here() { return done[current_device()]; }
+};
+// Makes `device` current for the lifetime of the guard (forward entry points: the caller's current device may differ
+// from the handle's) and restores the previous one.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t status = cudaSuccess;
+    explicit DeviceGuard(int device) {
+        status = cudaGetDevice(&prev);
+        if (status == cudaSuccess && prev != device) {
+            status = cudaSetDevice(device);
+            switched = status == cudaSuccess;
+        }
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+#define TTSB_DEVICE_GUARD(device)                    \
+    ::ttsb::DeviceGuard _ttsb_guard(device);         \
+    TTSB_CHECK_CUDA(_ttsb_guard.status)
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
@@ -104,6 +152,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+// non-blocking phase test: used to look at the NEXT ring stage's barrier before the current stage's MMAs are issued, so
+// the ~100-cycle barrier read overlaps the issue instead of heading every stage's dependent chain
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}\n"
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
@@ -255,6 +317,34 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
         : "r"(taddr)
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// Split form for software pipelining: issue the load of chunk c+1, then consume chunk c. The wait names the
+// destination registers as in/out operands so that no use of them can be scheduled above it.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float (&v)[32]) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+          "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+          "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(float (&v)[32]) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.wait::ld.sync.aligned;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]),
+          "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]),
+          "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]),
+          "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]),
+          "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+        :
+        : "memory");
 }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
     const uint32_t* r = reinterpret_cast<const uint32_t*>(v);

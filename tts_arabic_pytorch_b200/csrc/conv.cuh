@@ -88,9 +88,10 @@ struct ConvPairPlan {
 };
 // ok = 0 when the pair does not fit the fused kernel (caller falls back to two conv_forward launches)
 ConvPairPlan conv_pair_plan(const ConvLayer& L1, const ConvLayer& L2);
-// x: [B, T, C] raw (NOT pre-activated) input, also the residual. epi: bias/T/n_total/residual are
-// filled here; the caller sets lens/len_mul, out_raw or mrf_* (+ out_act), act_slope.
+// x: [B, T, C] input, also the residual: raw (in_act = 0: lrelu is applied in shared memory) or stored activated as
+// lrelu(x, slope) (in_act = 1: no transform, the residual add inverts the activation). epi: bias/T/n_total/residual are
+// filled here; the caller sets lens/len_mul, out_raw / out_act or mrf_*, act_slope.
 int conv_pair_forward(const ConvLayer& L1, const ConvLayer& L2, const ConvPairPlan& plan, const ConvRuntime& rt,
-                      const __half* x, int B, int T, float slope, EpiParams epi, cudaStream_t stream);
+                      const __half* x, int B, int T, float slope, EpiParams epi, cudaStream_t stream, int in_act = 0);
 
 }  // namespace ttsb

@@ -44,7 +44,9 @@ struct ConvPairArgs {
     int tt_rows;      // TT panel rows per chunk (multiple of 8, >= 128 + 2*h2)
     int x_slots, tt_slots;
     int w2_resident, b_stages;
-    int xform_final;  // 1: the final-epilogue groups run the lrelu transform (4 items ahead; needs x_slots >= 6), 0: the mid group
+    int stage2;       // 1: a second set of 8 x 2 KB staging tiles (residual transposes) follows the bias tile (run_epilogue_lean)
+    int in_act;       // 1: x is stored activated (lrelu(x)): the TMA panel IS conv1's operand — no in-place transform, the conv1
+                      // issuer waits for the panel itself; the final epilogue recovers x for the residual (EpiParams::res_inv)
     const __half* w1;
     const __half* w2;
     const float* bias1;
@@ -78,11 +80,22 @@ __device__ __forceinline__ void pair_transform_slot(const ConvPairArgs& args, ui
     if (tid == 0) tlp_mark(args, item, 1);
     const __half2 slope2 = __float2half2_rn(args.slope);
     const uint32_t base = smem_u32(slot);
-    for (int i = tid; i < ((args.debug & 1) ? 0 : units); i += 128) {
-        uint4 v = lds128(base + i * 16);
-        v.x = lrelu_h2(v.x, slope2); v.y = lrelu_h2(v.y, slope2);
-        v.z = lrelu_h2(v.z, slope2); v.w = lrelu_h2(v.w, slope2);
-        sts128(base + i * 16, v);
+    // four independent 16-byte units per thread and pass: loads first, then the math, then the stores. The shared-memory
+    // accessors are volatile asm, so a one-unit loop body is a serial load -> math -> store chain of ~110 cycles per
+    // unit (profiles/r01_s48_pair_two_final_groups.txt: ~1000 cycles per 17 KB panel for this group).
+    for (int i0 = tid; i0 < ((args.debug & 1) ? 0 : units); i0 += 128 * 4) {
+        uint4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (i0 + j * 128 < units) v[j] = lds128(base + (i0 + j * 128) * 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            v[j].x = lrelu_h2(v[j].x, slope2); v[j].y = lrelu_h2(v[j].y, slope2);
+            v[j].z = lrelu_h2(v[j].z, slope2); v[j].w = lrelu_h2(v[j].w, slope2);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (i0 + j * 128 < units) sts128(base + (i0 + j * 128) * 16, v[j]);
     }
     fence_proxy_async();
     __syncwarp();
@@ -230,7 +243,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 int sx = 0, b1 = 0, it = 0;
                 uint32_t pxl = 0, pe1 = 3;   // xl_full parity; per-buffer parity bits of acc1_empty (first lap passes)
                 for (int idx = blockIdx.x; idx < args.n_work; idx += grid, ++it) {
-                    mbar_wait(&xl_full[sx], pxl, args.err_flag, 304);
+                    mbar_wait(args.in_act ? &x_full[sx] : &xl_full[sx], pxl, args.err_flag, 304);
                     mbar_wait(&acc1_empty[b1], (pe1 >> b1) & 1u, args.err_flag, 305);
                     pe1 ^= 1u << b1;
                     tc_fence_after();
@@ -321,27 +334,40 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         int n_items = 0;
         for (int idx = blockIdx.x; idx < args.n_work; idx += grid) ++n_items;
         // x(it + la) is issued once conv1(it + la - x_slots) has completed; la = 0: the final groups transform
-        const int la = args.xform_final ? 0 : min(2, args.x_slots - 1);
+        const int la = args.in_act ? 0 : min(2, args.x_slots - 1);
         for (int j = 0; j < la && j < n_items; ++j) transform(j);
+        // lens[b] of the NEXT item is fetched one item ahead: with the SM's L1 carved out as shared memory the load is an
+        // L2 round trip (~700 cycles), and this group's item period is the pipeline's (round-2 timeline, gpurun r2_s1)
+        constexpr int kC = kTmemCols / 4;
+        auto len_of = [&](int idx) {
+            if (idx >= args.n_work || args.epi.lens == nullptr) return args.T;
+            return min(args.T, __ldg(args.epi.lens + idx / args.tiles_t) * args.epi.len_mul);
+        };
+        int len_nxt = len_of(blockIdx.x);
         for (int idx = blockIdx.x; idx < args.n_work; idx += grid, ++it) {
             const int b = idx / args.tiles_t;
             const int t0 = (idx - b * args.tiles_t) * args.m_out;
             const int t = t0 - args.h2 + m;
-            int len_rows = args.T;
-            if (args.epi.lens != nullptr) len_rows = min(len_rows, __ldg(args.epi.lens + b) * args.epi.len_mul);
+            const int len_rows = len_nxt;
+            len_nxt = len_of(idx + grid);
             const bool valid = t >= 0 && t < len_rows;
             mbar_wait(&acc1_full[b1], (pf >> b1) & 1u, args.err_flag, 310);
             pf ^= 1u << b1;
             tc_fence_after();
             if (m == 0) tlp_mark(args, it, 7);
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc1_col + b1 * kC;
+            // accumulator chunk c+1 is in flight while chunk c is converted (tcgen05.ld is asynchronous until its wait)
+            float v[2][32];
+            tmem_ld32_issue(taddr, v[0]);
             mbar_wait(&tt_empty[st], (pte >> st) & 1u, args.err_flag, 311);
             pte ^= 1u << st;
             if (m == 0) tlp_mark(args, it, 8);
             const uint32_t tt_base = smem_u32(smem_tt + st * ttslot_bytes) + m * row_bytes;
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc1_col + b1 * C;
-            for (int c0 = 0; c0 < C; c0 += 32) {
-                float v[32];
-                tmem_ld32(taddr + c0, v);
+#pragma unroll
+            for (int ci = 0; ci < kC / 32; ++ci) {
+                const int c0 = ci * 32;
+                tmem_ld_wait(v[ci & 1]);
+                if (ci + 1 < kC / 32) tmem_ld32_issue(taddr + c0 + 32, v[(ci + 1) & 1]);
                 const int chunk = c0 / args.chunk_k;
                 const int u0 = (c0 - chunk * args.chunk_k) >> 3;
 #pragma unroll
@@ -350,8 +376,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     bias8s(sb1 + (c0 + g * 8) * 4, bs);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const float y = v[g * 8 + j] + bs[j];
-                        a[j] = valid ? (y > 0.f ? y : y * slope) : 0.f;
+                        const float y = v[ci & 1][g * 8 + j] + bs[j];
+                        a[j] = valid ? fmaxf(y, y * slope) : 0.f;      // slope in (0, 1): max(y, slope * y) == lrelu(y)
                     }
                     if (!(args.debug & 2)) sts128(tt_base + chunk * ttp_bytes + ((u0 + g) ^ phase) * 16, pack8(a));
                 }
@@ -375,6 +401,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const int q = warp & 3;
         constexpr bool kMrf = kEpi == 2;
         uint8_t* stage = smem_stage + (warp - 8) * 2048;
+        uint8_t* stage_in = args.stage2 ? smem_stage + 8 * 2048 + 1024 + (warp - 8) * 2048 : nullptr;
         const int b2 = g;
         uint32_t par = 0;
         LeanPrefetch<kMrf> pre_cur, pre_nxt;
@@ -387,22 +414,6 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             lean_prefetch(args.epi, io, static_cast<long>(b0) * args.T + w0, 0, true, pre_cur, b0);
         }
         const bool tl_on = q == 0 && lane == 0;
-        // With a deep x ring the transform lives here, four items ahead of this group's own item (same parity, so each
-        // group transforms exactly the panels whose results it will finish): two groups x 3.1 k cycles per item leave
-        // more slack than the mid group has. conv1(j) then waits for final(j - 4), four items behind it anyway.
-        int n_items = 0;
-        for (int idx = blockIdx.x; idx < args.n_work; idx += grid) ++n_items;
-        const int tid = threadIdx.x - (8 + 4 * g) * 32;
-        const int units = xslot_bytes >> 4;
-        auto transform = [&](int j) {
-            const int sx = j % args.x_slots;
-            pair_transform_slot(args, smem_x + sx * xslot_bytes, units, &x_full[sx], &xl_full[sx],
-                                static_cast<uint32_t>(j / args.x_slots) & 1u, tid, j);
-        };
-        if (args.xform_final) {
-            if (g < n_items) transform(g);
-            if (g + 2 < n_items) transform(g + 2);
-        }
         int it = g;
         for (int idx = idx_first; idx < args.n_work; idx += 2 * grid, it += 2) {
             const int b = idx / args.tiles_t;
@@ -434,13 +445,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 // the MRF variant, whose extra live chunks would spill (and a spill reload is an L2 round trip here)
                 if (!kMrf) lean_prefetch(args.epi, nio, static_cast<long>(nb) * args.T + nw0, 0, nvalid, pre_nxt, nb);
                 run_epilogue_lean<kMrf, true, !kMrf>(args.epi, acc, b, t, 0, C, wait_acc, drained, stage, pre_cur, t0 + args.m_out,
-                                        smem_u32(sbias2));
+                                        smem_u32(sbias2), nullptr, nullptr, nullptr, stage_in);
                 if (kMrf) lean_prefetch(args.epi, nio, static_cast<long>(nb) * args.T + nw0, 0, nvalid, pre_nxt, nb);
             }
             pre_cur = pre_nxt;
             if (tl_on) tlp_mark(args, it, 12);
             par ^= 1;
-            if (args.xform_final && it + 4 < n_items) transform(it + 4);
         }
     }
     tc_fence_before();
@@ -452,7 +462,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 // host
 // ------------------------------------------------------------------------------------------------
 static const size_t kPairSmemMax = 232448;
-static const size_t kPairFixed = 1024 /*alignment*/ + 1024 /*barriers + tmem slot*/ + 16384 /*staging: 8 warps*/ + 512 /*biases*/ + 256;
+static const size_t kPairFixed = 1024 /*alignment*/ + 1024 /*barriers + tmem slot*/ + 16384 /*staging: 8 warps*/ + 1024 /*biases*/ + 256;
 
 ConvPairPlan conv_pair_plan(const ConvLayer& L1, const ConvLayer& L2) {
     ConvPairPlan p;
@@ -506,11 +516,11 @@ ConvPairPlan conv_pair_plan(const ConvLayer& L1, const ConvLayer& L2) {
 
 template <int kCols, int kEpi>
 static int launch_pair(const CUtensorMap& tm, const ConvPairArgs& a, int grid, size_t smem, cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (!configured.here()) {
         TTSB_CHECK_CUDA(cudaFuncSetAttribute(conv_pair_kernel<kCols, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(kPairSmemMax)));
-        configured = true;
+        configured.here() = true;
     }
     conv_pair_kernel<kCols, kEpi><<<grid, kPairThreads, smem, s>>>(tm, a);
     count_launch();
@@ -519,7 +529,7 @@ static int launch_pair(const CUtensorMap& tm, const ConvPairArgs& a, int grid, s
 }
 
 int conv_pair_forward(const ConvLayer& L1, const ConvLayer& L2, const ConvPairPlan& plan, const ConvRuntime& rt,
-                      const __half* x, int B, int T, float slope, EpiParams epi, cudaStream_t stream) {
+                      const __half* x, int B, int T, float slope, EpiParams epi, cudaStream_t stream, int in_act) {
     TTSB_REQUIRE(plan.ok, "conv pair plan is not feasible");
     TTSB_REQUIRE(B > 0 && T > 0, "empty batch");
     TTSB_REQUIRE(slope > 0.f && slope < 1.f, "leaky-relu slope must be in (0, 1)");
@@ -538,9 +548,10 @@ int conv_pair_forward(const ConvLayer& L1, const ConvLayer& L2, const ConvPairPl
     a.rows_panel = plan.rows_panel; a.tt_rows = plan.tt_rows;
     a.x_slots = plan.x_slots; a.tt_slots = plan.tt_slots;
     a.w2_resident = plan.w2_resident; a.b_stages = plan.b_stages;
-    // measured neutral against the mid-group transform (profiles/r01_s48_pair_two_final_groups.txt): off unless asked for
-    static const int xform_final = getenv("TTSB_PAIR_XFORM_FINAL") ? atoi(getenv("TTSB_PAIR_XFORM_FINAL")) : 0;
-    a.xform_final = (xform_final && plan.x_slots >= 6) ? 1 : 0;
+    a.in_act = in_act ? 1 : 0;
+    // the final epilogue's TMA-less stores still go LDS -> STG through the staging tile; a second tile set only pays with
+    // TMA output, which conv_pair does not use yet
+    a.stage2 = 0;
     a.w1 = L1.w_packed; a.w2 = L2.w_packed;
     a.bias1 = L1.bias;
     a.slope = slope;
@@ -553,6 +564,7 @@ int conv_pair_forward(const ConvLayer& L1, const ConvLayer& L2, const ConvPairPl
     epi.bias = L2.bias;
     epi.residual = x;
     epi.ld_res = plan.C;
+    epi.res_inv = in_act ? 1.f / slope : 1.f;
     a.epi = epi;
     const int grid = std::min(num_sms(), a.n_work);
     const bool mrf = epi.mrf_mode != MRF_NONE;

@@ -232,11 +232,11 @@ static PFN_encodeTiled get_encode_fn() {
 
 template <int kCols>
 static int launch_one(const CUtensorMap& tm, const ConvTcArgs& a, dim3 grid, size_t smem, cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (!configured.here()) {
         TTSB_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<kCols>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-        configured = true;
+        configured.here() = true;
     }
     conv_tc_kernel<kCols><<<grid, 192, smem, s>>>(tm, a);
     count_launch();

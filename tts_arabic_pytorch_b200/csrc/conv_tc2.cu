@@ -44,6 +44,9 @@ struct ConvTc2Args {
     int halo_lo;
     const __half* w;
     int tma_out;       // bit 0 / 1 / 2: out_raw / out_act / mrf_buf leave through TMA stores (lean epilogue)
+    int stage2;        // lean epilogue: a second set of 4 x 2 KB staging tiles (transposes) next to the output tiles
+    int sbias_bytes;   // size of the parameter tile region that precedes them
+    int issue_mode;    // MMA issuer: 0 generic loops, 1 straight-line K steps, 2 + the next weight stage's barrier is tested ahead
     int params_smem;   // general epilogue: [bias][ln_g][ln_b][head_w] of this N tile staged in shared memory (room permitting)
     int* err_flag;
     long long* timeline;   // debug (tools/timeline.py): 64 clock64() slots per CTA for the first 256 CTAs, or null
@@ -197,6 +200,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             uint32_t pa = 0, pb = 0;      // parity to wait on the FULL barriers
             uint32_t pe0 = 1, pe1 = 1;    // parity to wait on tmem_empty[0/1]
             const int buf_cols = args.rpp * args.n_tile;
+            const bool fast_issue = args.issue_mode != 0 && args.rpp == 1 && args.n_sub == 1 && ksteps == 4;
+            bool b_ready = false;
             if (args.resident) {
                 mbar_wait(w_full, 0, args.err_flag, 207);
                 tc_fence_after();
@@ -209,6 +214,53 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 if (buf) pe1 ^= 1; else pe0 ^= 1;
                 const uint32_t d_tmem = tmem_base + buf * buf_cols;
                 uint32_t accumulate = 0;
+                if (fast_issue) {
+                    // One row tile, one N sub-tile, K = 64 per (chunk, tap) — every C >= 128 vocoder layer. The generic
+                    // loops below cost ~115 SASS instructions per tap and ~250 cycles per tcgen05.mma for the issuing
+                    // thread, twice the MMA's own time (profiles/r01_s57_issue_overhead.txt). Here the four K steps go out
+                    // back to back (the 14-bit address field cannot carry: a view start + 96 B is still a shared-memory
+                    // address) and, in mode 2, the barrier of the NEXT weight stage is tested before this stage's MMAs are
+                    // issued, which takes the barrier read off the per-stage dependent chain.
+                    const uint64_t hi = static_cast<uint64_t>(desc_hi) << 32;
+                    for (int c = 0; c < args.n_chunks; ++c) {
+                        mbar_wait(&full_a[sa], pa, args.err_flag, 204);
+                        uint32_t al = ((a_lo0 + sa * panel_u) & 0x3FFFu) | lo_flag;
+                        const int a_slot0 = sa;
+                        if (++sa == args.a_slots) { sa = 0; pa ^= 1; }
+                        tc_fence_after();
+                        if (c == 0 && tl_i < 7) tl2_mark(args, 8 + tl_i * 8 + 1);
+                        for (int tap = 0; tap < args.n_taps; ++tap) {
+                            uint32_t bl;
+                            int cur = 0;
+                            if (args.resident) {
+                                bl = ((b_lo0 + (c * args.n_taps + tap) * btile_u) & 0x3FFFu) | lo_flag;
+                            } else {
+                                if (!b_ready) mbar_wait(&full_b[sb], pb, args.err_flag, 205);
+                                tc_fence_after();
+                                bl = ((b_lo0 + sb * btile_u) & 0x3FFFu) | lo_flag;
+                                cur = sb;
+                                if (++sb == args.b_stages) { sb = 0; pb ^= 1; }
+                            }
+                            umma_f16(d_tmem, hi | al, hi | bl, idesc, accumulate);
+                            umma_f16(d_tmem, hi | (al + 2u), hi | (bl + 2u), idesc, 1u);
+                            umma_f16(d_tmem, hi | (al + 4u), hi | (bl + 4u), idesc, 1u);
+                            umma_f16(d_tmem, hi | (al + 6u), hi | (bl + 6u), idesc, 1u);
+                            al = ((al + tap_u) & 0x3FFFu) | lo_flag;
+                            accumulate = 1;
+                            if (!args.resident) {
+                                // look at the next stage while this stage's MMAs execute
+                                b_ready = args.issue_mode >= 2 && mbar_test_wait(&full_b[sb], pb);
+                                if (csize == 2) umma_commit_multicast(&empty_b[cur], cmask);
+                                else umma_commit(&empty_b[cur]);
+                            }
+                        }
+                        umma_commit(&empty_a[a_slot0]);
+                    }
+                    umma_commit(&tmem_full[buf]);
+                    if (tl_i < 7) tl2_mark(args, 8 + tl_i * 8 + 2);
+                    if (args.acc_bufs == 2) buf ^= 1;
+                    continue;
+                }
                 for (int c = 0; c < args.n_chunks; ++c) {
                     uint32_t a_lo[4];
                     int a_slot[4];
@@ -275,6 +327,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         int tl_i = 0;
         const bool tl_on = threadIdx.x == 64;
         uint8_t* stage = smem_stage + q * 2048;
+        uint8_t* stage_in = args.stage2 ? smem_stage + 4 * 2048 + args.sbias_bytes + q * 2048 : nullptr;
         // lean path: the first residual / MRF chunk of the NEXT work item is requested before this
         // item's accumulator is waited for, so its latency hides behind a whole tile
         constexpr bool kLean = kEpi != 0;
@@ -326,7 +379,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     lean_prefetch(args.epi, nio, static_cast<long>(nb) * args.T + nw0, n_base, nvalid, pre_nxt, nb);
                     run_epilogue_lean<kMrf, true, !(kMrf && kMinBlocks >= 2)>(args.epi, acc, b, t, n_base, args.n_tile, wait_acc, drained, stage, pre_cur,
                                             0x7fffffff, smem_u32(sbias), (args.tma_out & 1) ? &tmap_raw : nullptr,
-                                            (args.tma_out & 2) ? &tmap_act : nullptr, (args.tma_out & 4) ? &tmap_mrf : nullptr);
+                                            (args.tma_out & 2) ? &tmap_act : nullptr, (args.tma_out & 4) ? &tmap_mrf : nullptr, stage_in);
                     pre_cur = pre_nxt;
                 } else {
                     long long* dbg = (tl_on && args.timeline != nullptr && blockIdx.x < 256 && tl_i < 7)
@@ -403,14 +456,13 @@ int get_act_tensor_map(const __half* in, int ld_in, int B, int T, int cin, int c
 }
 
 int num_sms() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
+    static int n[kMaxDevices] = {};
+    const int dev = current_device();
+    if (!n[dev]) {
+        cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (n[dev] <= 0) n[dev] = 148;
     }
-    return n;
+    return n[dev];
 }
 
 struct OutMaps {
@@ -419,11 +471,11 @@ struct OutMaps {
 
 template <int kCols, int kMinBlocks, int kEpi>
 static int launch_two_impl(const CUtensorMap& tm, const ConvTc2Args& a, int grid, size_t smem, cudaStream_t s, const OutMaps& om) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (!configured.here()) {
         TTSB_CHECK_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<kCols, kMinBlocks, kEpi>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-        configured = true;
+        configured.here() = true;
     }
     if (a.cluster == 2) {
         cudaLaunchConfig_t cfg = {};
@@ -497,6 +549,8 @@ int conv_forward_tc2(const ConvLayer& L, const ConvRuntime& rt, const __half* in
     }
     a.w = L.w_packed; a.err_flag = rt.err_flag; a.epi = epi;
     a.timeline = rt.timeline;
+    static const int issue_mode = getenv("TTSB_ISSUE") ? atoi(getenv("TTSB_ISSUE")) : 2;
+    a.issue_mode = issue_mode;
 
     // lean epilogue: outputs leave through TMA stores of 32-row x 32-column blocks (64-byte swizzle = the staging
     // tiles' XOR pattern); the maps are the activation map function with a 32 x 32 box over [B][T][n_total]
@@ -526,6 +580,18 @@ int conv_forward_tc2(const ConvLayer& L, const ConvRuntime& rt, const __half* in
         if (L.smem_bytes2 + extra <= limit && L.smem_bytes2 + extra <= 232448) {
             a.params_smem = 1;
             smem_bytes += extra;
+        }
+    }
+    // second staging tile set for the lean epilogue's transposes, room permitting (see run_epilogue_lean)
+    a.stage2 = 0;
+    a.sbias_bytes = static_cast<int>(2048 + (smem_bytes - L.smem_bytes2));
+    {
+        static const int want_stage2 = getenv("TTSB_STAGE2") ? atoi(getenv("TTSB_STAGE2")) : 1;
+        const size_t limit = std::min<size_t>(232448, 233472 / L.occ2 - 1024);
+        if (want_stage2 && host_epi_is_lean(epi) && (epi.residual != nullptr || epi.mrf_mode != MRF_NONE) && a.tma_out != 0 &&
+            smem_bytes + 8192 <= limit) {
+            a.stage2 = 1;
+            smem_bytes += 8192;
         }
     }
     // CTA pairs share streamed weight tiles through TMA multicast (halves the L2->SM weight traffic that

@@ -131,6 +131,7 @@ size_t ttsb_denoiser_workspace_bytes(int B, int n_max) {
 
 int ttsb_denoiser_forward(const float* d_wav, const int32_t* d_n_samples, int B, int n_max, const float* d_bias_spec,
                           float strength, float* d_out, void* d_workspace, size_t workspace_bytes, void* stream_) {
+    return guarded_call([&]() -> int {
     TTSB_REQUIRE(d_wav && d_n_samples && d_bias_spec && d_out && d_workspace, "null argument");
     TTSB_REQUIRE(B > 0 && n_max > 0, "empty batch");
     TTSB_REQUIRE(workspace_bytes >= ttsb_denoiser_workspace_bytes(B, n_max), "workspace too small");
@@ -146,6 +147,7 @@ int ttsb_denoiser_forward(const float* d_wav, const int32_t* d_n_samples, int B,
     count_launch();
     TTSB_CHECK_CUDA(cudaGetLastError());
     return 0;
+    });
 }
 
 }  // extern "C"

@@ -26,6 +26,11 @@ struct EpiParams {
     const float* bias = nullptr;    // [n_total]
     const __half* residual = nullptr;
     int ld_res = 0;
+    // residual stored ACTIVATED: the buffer holds lrelu(x, s) and the epilogue adds x = min(r, r * res_inv) with
+    // res_inv = 1 / s (1 = the buffer holds x itself). lrelu is invertible and both forms carry the same fp16 relative
+    // error, so a tensor that feeds a conv as lrelu(x) AND a later residual add as x (every ResBlock1 input,
+    // hifigan/models.py:46-53) is kept in HBM once, activated, instead of twice.
+    float res_inv = 1.f;
     int pre_ln_relu = 0;
     const float* ln_g = nullptr;    // LayerNorm over n_total columns (needs a single N tile)
     const float* ln_b = nullptr;
@@ -323,7 +328,7 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& e, const Acc& acc,
                 unpack8(res_cur.q[g], r);
                 param8(0, e.bias, n, bs);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) x[j] = v[g * 8 + j] + bs[j] + r[j];
+                for (int j = 0; j < 8; ++j) x[j] = v[g * 8 + j] + bs[j] + fminf(r[j], r[j] * e.res_inv);
             }
             if (e.out_f32_t && e.f32_unmasked && row_ok) {
 #pragma unroll
@@ -405,7 +410,12 @@ __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc&
                                                   int n_tile, WaitFn wait_acc, DrainFn acc_drained, uint8_t* stage,
                                                   const LeanPrefetch<kMrf>& pre, int t_end = 0x7fffffff,
                                                   uint32_t bias_saddr = 0, const CUtensorMap* tm_raw = nullptr,
-                                                  const CUtensorMap* tm_act = nullptr, const CUtensorMap* tm_mrf = nullptr) {
+                                                  const CUtensorMap* tm_act = nullptr, const CUtensorMap* tm_mrf = nullptr,
+                                                  uint8_t* stage_in = nullptr) {
+    // stage_in: a second 2 KB tile of this warp for the residual / MRF row transposes. With ONE tile every transpose has
+    // to wait until the TMA store issued just before it (the previous chunk's output) has finished reading the tile —
+    // a full TMA read latency per chunk on the epilogue's critical path (round-2 timeline: ~2000 cycles per chunk).
+    // With two tiles the output tile is next written a whole chunk after its store was issued. null = share `stage`.
     // tm_*: when non-null the matching output leaves through TMA stores of 32 x 32 blocks (RowIO::store_tma)
     // kSmemBias: bias_saddr is the shared-memory address of this N tile's bias floats (else e.bias through __ldg)
     // t_end: exclusive row limit of this tile's stores (conv_pair tiles own fewer than 128 rows)
@@ -414,6 +424,8 @@ __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc&
     const long row0 = static_cast<long>(b) * e.T + warp_row0;
     const bool in_len = t < pre.len_rows;
     RowIO io{stage, lane, min(32, max(0, min(e.T, t_end) - warp_row0))};
+    RowIO io_in{stage_in != nullptr ? stage_in : stage, lane, io.rows_valid};
+    const bool shared_tile = stage_in == nullptr || stage_in == stage;
     const bool use_res = e.residual != nullptr;
     const bool use_mrf = kMrf && (e.mrf_mode == MRF_ADD || e.mrf_mode == MRF_LAST);
     const bool mrf_store = kMrf && (e.mrf_mode == MRF_FIRST || e.mrf_mode == MRF_ADD);
@@ -421,6 +433,7 @@ __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc&
     __half* mrf_blk = e.mrf_buf + row0 * e.n_total + n_base;
     const float mscale = kMrf ? e.mrf_scale : 1.f;
     const float slope = e.act_slope;
+    const float rinv = e.res_inv;
 
     Chunk32 res_cur = pre.res, mrf_cur;
     if (kMrf) io.request(mrf_blk, e.n_total, use_mrf, mrf_cur);
@@ -441,8 +454,8 @@ __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc&
             if (kMrf) io.request(mrf_blk + c0, e.n_total, use_mrf, mrf_cur);
         }
         const bool tma_out = tm_raw != nullptr || tm_act != nullptr || tm_mrf != nullptr;
-        if (use_res) io.to_row(res_cur, tma_out);
-        if (kMrf && use_mrf) io.to_row(mrf_cur, tma_out);
+        if (use_res) io_in.to_row(res_cur, tma_out && shared_tile);
+        if (kMrf && use_mrf) io_in.to_row(mrf_cur, tma_out && shared_tile);
         __syncwarp();
         acc.load(c0, v);
         if (!more) acc_drained();
@@ -455,7 +468,7 @@ __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc&
             if (kSmemBias) bias8s(bias_saddr + (c0 + g * 8) * 4, bs);
             else bias8(e.bias, n_base + c0 + g * 8, bs);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = v[g * 8 + j] + bs[j] + r[j];
+            for (int j = 0; j < 8; ++j) x[j] = v[g * 8 + j] + bs[j] + fminf(r[j], r[j] * rinv);   // rinv >= 1: inverse lrelu
             if (any_masked) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) x[j] = in_len ? x[j] : 0.f;

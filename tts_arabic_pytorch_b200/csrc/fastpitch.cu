@@ -228,14 +228,16 @@ extern "C" {
 
 int ttsb_fastpitch_create(const ttsb_fastpitch_config_t* cfg, const ttsb_tensor_t* weights, int n_weights,
                           int device, ttsb_fastpitch_t** out) {
+    return guarded_call([&]() -> int {
     TTSB_REQUIRE(cfg && weights && out, "null argument");
     TTSB_REQUIRE(cfg->d_head == 64, "attention kernel is specialised for one head of 64");
     TTSB_REQUIRE(cfg->d_model % 64 == 0 && cfg->d_inner % 256 == 0 && cfg->pred_filter % 64 == 0 &&
                      cfg->d_model <= 512 && cfg->pred_filter <= 512, "channel sizes");
     TTSB_REQUIRE(cfg->conv_kernel == 3 && cfg->pred_kernel == 3, "kernel size 3 expected");
-    TTSB_CHECK_CUDA(cudaSetDevice(device));
+    TTSB_DEVICE_GUARD(device);
     TensorTable tab(weights, n_weights);
-    ttsb_fastpitch* h = new ttsb_fastpitch();
+    std::unique_ptr<ttsb_fastpitch, void (*)(ttsb_fastpitch*)> owner(new ttsb_fastpitch(), ttsb_fastpitch_destroy);
+    ttsb_fastpitch* h = owner.get();
     h->cfg = *cfg;
     h->device = device;
     h->mel_ld = round_up(cfg->n_mel_channels, 64);
@@ -276,8 +278,9 @@ int ttsb_fastpitch_create(const ttsb_fastpitch_config_t* cfg, const ttsb_tensor_
         TTSB_REQUIRE(pw->shape[0] == cfg->n_mel_channels && pw->shape[1] == D, "proj shape");
         TTSB_PROPAGATE(make_linear_layer(h->proj, pw->h_data, pb->h_data, cfg->n_mel_channels, D, h->mel_ld, 0));
     }
-    *out = h;
+    *out = owner.release();
     return 0;
+    });
 }
 
 void ttsb_fastpitch_destroy(ttsb_fastpitch_t* h) {
@@ -305,10 +308,12 @@ size_t ttsb_fastpitch_workspace_bytes(const ttsb_fastpitch_t* h, int B, int L, i
 int ttsb_fastpitch_encode(ttsb_fastpitch_t* h, const int64_t* d_ids, int B, int L, int speaker,
                           float* d_log_dur, float* d_pitch, void* d_state, void* d_workspace,
                           size_t workspace_bytes, void* stream_) {
+    return guarded_call([&]() -> int {
     TTSB_REQUIRE(h && d_ids && d_log_dur && d_pitch && d_state && d_workspace, "null argument");
     TTSB_REQUIRE(B > 0 && L > 0, "empty batch");
     TTSB_REQUIRE(workspace_bytes >= ttsb_fastpitch_workspace_bytes(h, B, L, 0), "workspace too small");
     TTSB_REQUIRE(speaker < h->cfg.n_speakers, "speaker id out of range");
+    TTSB_DEVICE_GUARD(h->device);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     ConvRuntime rt;
     TTSB_PROPAGATE(get_conv_runtime(simt_elems(h, B, L), rt));
@@ -322,6 +327,7 @@ int ttsb_fastpitch_encode(ttsb_fastpitch_t* h, const int64_t* d_ids, int B, int 
     TTSB_PROPAGATE(run_predictor(h, h->dur, rt, st.x, st.lens, B, L, sc, d_log_dur, stream));
     TTSB_PROPAGATE(run_predictor(h, h->pitch, rt, st.x, st.lens, B, L, sc, d_pitch, stream));
     return 0;
+    });
 }
 
 int ttsb_fastpitch_condition(ttsb_fastpitch_t* h, int B, int L, const float* d_log_dur,
@@ -329,9 +335,11 @@ int ttsb_fastpitch_condition(ttsb_fastpitch_t* h, int B, int L, const float* d_l
                              float pace, float max_duration, float* d_dur_pred, float* d_energy_pred,
                              int64_t* d_dec_lens, void* d_state, void* d_workspace, size_t workspace_bytes,
                              void* stream_) {
+    return guarded_call([&]() -> int {
     TTSB_REQUIRE(h && d_log_dur && d_pitch_in && d_dur_pred && d_dec_lens && d_state && d_workspace, "null argument");
     TTSB_REQUIRE(workspace_bytes >= ttsb_fastpitch_workspace_bytes(h, B, L, 0), "workspace too small");
     TTSB_REQUIRE(pace > 0.f, "pace must be positive");
+    TTSB_DEVICE_GUARD(h->device);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     ConvRuntime rt;
     TTSB_PROPAGATE(get_conv_runtime(simt_elems(h, B, L), rt));
@@ -353,13 +361,16 @@ int ttsb_fastpitch_condition(ttsb_fastpitch_t* h, int B, int L, const float* d_l
     TTSB_PROPAGATE(launch_durations(d_log_dur, d_dur_tgt, pace, max_duration, B, L, d_dur_pred, st.cum,
                                     st.dec_lens, d_dec_lens, stream));
     return 0;
+    });
 }
 
 int ttsb_fastpitch_decode(ttsb_fastpitch_t* h, int B, int L, int T, float* d_mel, void* d_mel_cl,
                           void* d_state, void* d_workspace, size_t workspace_bytes, void* stream_) {
+    return guarded_call([&]() -> int {
     TTSB_REQUIRE(h && d_mel && d_state && d_workspace, "null argument");
     TTSB_REQUIRE(B > 0 && L > 0 && T > 0, "empty batch");
     TTSB_REQUIRE(workspace_bytes >= ttsb_fastpitch_workspace_bytes(h, B, L, T), "workspace too small");
+    TTSB_DEVICE_GUARD(h->device);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     ConvRuntime rt;
     TTSB_PROPAGATE(get_conv_runtime(simt_elems(h, B, T), rt));
@@ -376,6 +387,7 @@ int ttsb_fastpitch_decode(ttsb_fastpitch_t* h, int B, int L, int T, float* d_mel
     }
     TTSB_PROPAGATE(conv_forward(h->proj, rt, sc.x, D, B, T, e, stream));
     return 0;
+    });
 }
 
 }  // extern "C"

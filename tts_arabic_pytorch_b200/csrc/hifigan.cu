@@ -4,14 +4,18 @@
 //   conv_pre -> 4 x [ lrelu(0.1) -> ConvTranspose1d -> mean_j ResBlock1_j ] -> lrelu(0.01) -> conv_post -> tanh
 //
 // Data flow per stage (all tensors channel-last fp16 [B, len, C]):
-//   ups      : in  = act(prev)          -> X0 (raw), LX0 = lrelu(X0)
-//   resblock j, pair p (dilation d_p):
-//     conv1  : in  = p==0 ? LX0 : LXA   -> TT = lrelu(conv + b)
-//     conv2  : in  = TT, residual = p==0 ? X0 : XA
-//              p<2 : XA = v, LXA = lrelu(v)
+// Every ResBlock1 tensor x feeds a conv as lrelu(x) and, one conv later, a residual add as x. Both uses are served by ONE
+// stored tensor, the activated one: the residual add inverts the (invertible) leaky-relu in the epilogue
+// (EpiParams::res_inv), so no tensor is written twice and no launch needs an activation pass over its input
+// (TTSB_ACT_CHAIN=0 restores the round-1 raw + activated pairs).
+//   ups      : in  = act(prev)          -> LX0 = lrelu(X0)
+//   resblock j, pair p (dilation d_p), LX_p = LX0 / LXA / LXB:
+//     conv1  : in  = LX_p               -> TT = lrelu(conv + b)
+//     conv2  : in  = TT, residual = inv_lrelu(LX_p)
+//              p<2 : LX_{p+1} = lrelu(v)
 //              p==2: MRF accumulate v/3 into XS; on the last resblock emit NXT = lrelu(XS_total)
-// Pairs with a feasible ConvPairPlan (C <= 64) run conv1+conv2 as ONE launch (conv_pair.cu): raw tensors only,
-//     pair   : in = p==0 ? X0 : (p==1 ? XA : XB), out = p==0 ? XA : XB  (p==2: MRF accumulate as above)
+// Pairs with a feasible ConvPairPlan (C <= 64) run conv1+conv2 as ONE launch (conv_pair.cu):
+//     pair   : in = LX_p, out = LX_{p+1}  (p==2: MRF accumulate as above)
 // Every epilogue zeroes rows beyond the utterance's own length so that a padded batch sees the
 // same zero padding as the reference's per-utterance calls (models/fastpitch/networks.py:340-345).
 #include <cstdlib>
@@ -51,24 +55,26 @@ GlobalRuntime& global_runtime() {
 
 int get_conv_runtime(size_t simt_elems, ConvRuntime& rt) {
     GlobalRuntime& g = global_runtime();
-    if (!g.err_flag) {
-        TTSB_CHECK_CUDA(cudaMalloc(&g.err_flag, sizeof(int)));
-        TTSB_CHECK_CUDA(cudaMemset(g.err_flag, 0, sizeof(int)));
+    const int dev = current_device();
+    if (!g.err_flag[dev]) {
+        TTSB_CHECK_CUDA(cudaMalloc(&g.err_flag[dev], sizeof(int)));
+        TTSB_CHECK_CUDA(cudaMemset(g.err_flag[dev], 0, sizeof(int)));
     }
-    if (g.impl == IMPL_SIMT && g.simt_scratch_elems < simt_elems) {
+    if (g.impl == IMPL_SIMT && g.simt_scratch_elems[dev] < simt_elems) {
         // check path only: grows outside any timed region
         TTSB_CHECK_CUDA(cudaDeviceSynchronize());
-        if (g.simt_scratch) cudaFree(g.simt_scratch);
-        g.simt_scratch = nullptr;
-        TTSB_CHECK_CUDA(cudaMalloc(&g.simt_scratch, simt_elems * sizeof(float)));
-        g.simt_scratch_elems = simt_elems;
+        if (g.simt_scratch[dev]) cudaFree(g.simt_scratch[dev]);
+        g.simt_scratch[dev] = nullptr;
+        g.simt_scratch_elems[dev] = 0;
+        TTSB_CHECK_CUDA(cudaMalloc(&g.simt_scratch[dev], simt_elems * sizeof(float)));
+        g.simt_scratch_elems[dev] = simt_elems;
     }
     rt.impl = g.impl;
     rt.desc_mode = g.desc_mode;
     rt.tc_version = g.desc_mode != 0 ? 1 : g.tc_version;   // descriptor probes exist only in v1
-    rt.err_flag = g.err_flag;
-    rt.simt_scratch = g.simt_scratch;
-    rt.simt_scratch_elems = g.simt_scratch_elems;
+    rt.err_flag = g.err_flag[dev];
+    rt.simt_scratch = g.simt_scratch[dev];
+    rt.simt_scratch_elems = g.simt_scratch_elems[dev];
     rt.timeline = g.timeline;
     return 0;
 }
@@ -127,12 +133,15 @@ extern "C" {
 
 int ttsb_hifigan_create(const ttsb_hifigan_config_t* cfg, const ttsb_tensor_t* weights, int n_weights,
                         int device, ttsb_hifigan_t** out) {
+    return guarded_call([&]() -> int {
     TTSB_REQUIRE(cfg && weights && out, "null argument");
-    TTSB_CHECK_CUDA(cudaSetDevice(device));
+    TTSB_DEVICE_GUARD(device);
     TTSB_REQUIRE(cfg->num_kernels >= 1 && cfg->num_kernels <= 8 && cfg->num_upsamples >= 1 && cfg->num_upsamples <= 8,
                  "config ranges");
     TensorTable tab(weights, n_weights);
-    ttsb_hifigan* h = new ttsb_hifigan();
+    // owned until the end: an early return (bad checkpoint) must not leak the handle or its device buffers
+    std::unique_ptr<ttsb_hifigan, void (*)(ttsb_hifigan*)> owner(new ttsb_hifigan(), ttsb_hifigan_destroy);
+    ttsb_hifigan* h = owner.get();
     h->cfg = *cfg;
     h->device = device;
     if (const char* e = getenv("TTSB_HIFIGAN_CHUNK_FRAMES")) h->chunk_frames = atoi(e) > 0 ? atoi(e) : h->chunk_frames;
@@ -190,8 +199,9 @@ int ttsb_hifigan_create(const ttsb_hifigan_config_t* cfg, const ttsb_tensor_t* w
         TTSB_PROPAGATE(upload_f32(wt.data(), wt.size(), &h->post_w));
         h->post_b = b->h_data[0];
     }
-    *out = h;
+    *out = owner.release();
     return 0;
+    });
 }
 
 void ttsb_hifigan_destroy(ttsb_hifigan_t* h) {
@@ -224,10 +234,12 @@ size_t ttsb_hifigan_workspace_bytes(const ttsb_hifigan_t* h, int B, int T) {
 int ttsb_hifigan_forward(ttsb_hifigan_t* h, const float* d_mel_f32, const void* d_mel_cl,
                          const int32_t* d_lens, int B, int T, float* d_wav, void* d_workspace,
                          size_t workspace_bytes, void* stream_) {
+    return guarded_call([&]() -> int {
     TTSB_REQUIRE(h && d_wav && d_workspace, "null argument");
     TTSB_REQUIRE((d_mel_f32 != nullptr) != (d_mel_cl != nullptr), "exactly one mel input");
     TTSB_REQUIRE(B > 0 && T > 0, "empty batch");
     TTSB_REQUIRE(workspace_bytes >= ttsb_hifigan_workspace_bytes(h, B, T), "workspace too small");
+    TTSB_DEVICE_GUARD(h->device);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const ttsb_hifigan_config_t& cfg = h->cfg;
     const int bc_max = chunk_batch(h, B, T);
@@ -241,7 +253,10 @@ int ttsb_hifigan_forward(ttsb_hifigan_t* h, const float* d_mel_f32, const void* 
     __half *NXT[2] = {buf[0], buf[1]}, *X0 = buf[2], *LX0 = buf[3], *TT = buf[4], *XA = buf[5], *LXA = buf[6],
            *XS = buf[7];
     __half* XB = TT;   // a resblock is either fused (X0 -> XA -> XB) or not (LX0/TT/XA/LXA); they run one after another
+    __half* LXB = XA;  // activated chain: LX0 -> LXA -> LXB (XA and X0 are unused then)
     const bool use_pair = rt.impl == IMPL_TC && rt.tc_version == 2;
+    static const bool act_chain = getenv("TTSB_ACT_CHAIN") ? atoi(getenv("TTSB_ACT_CHAIN")) != 0 : true;
+    const float kSlope = 0.1f;   // LRELU_SLOPE (hifigan/models.py:9)
 
     for (int b0 = 0; b0 < B; b0 += bc_max) {
         const int bc = std::min(bc_max, B - b0);
@@ -270,9 +285,13 @@ int ttsb_hifigan_forward(ttsb_hifigan_t* h, const float* d_mel_f32, const void* 
             {
                 EpiParams e;
                 e.lens = lens; e.len_mul = up;
-                e.out_raw = X0; e.ld_raw = s * C;
-                if (any_unfused) { e.out_act = LX0; e.ld_act = s * C; }
-                e.act_slope = 0.1f;
+                if (act_chain) {
+                    e.out_act = LX0; e.ld_act = s * C;
+                } else {
+                    e.out_raw = X0; e.ld_raw = s * C;
+                    if (any_unfused) { e.out_act = LX0; e.ld_act = s * C; }
+                }
+                e.act_slope = kSlope;
                 TTSB_PROPAGATE(conv_forward(h->ups[i], rt, NXT[cur], cin, bc, T * up, e, stream));
             }
             up *= s;
@@ -283,19 +302,28 @@ int ttsb_hifigan_forward(ttsb_hifigan_t* h, const float* d_mel_f32, const void* 
                     const int idx = (i * cfg.num_kernels + j) * 3 + p;
                     // a resblock is fused as a whole or not at all (its three pairs share k and C)
                     const bool fused = use_pair && h->pair[idx - p].ok && h->pair[idx - p + 1].ok && h->pair[idx - p + 2].ok;
+                    __half* lx_in = p == 0 ? LX0 : (p == 1 ? LXA : LXB);      // activated chain
                     if (!fused) {
                         EpiParams e;
                         e.lens = lens; e.len_mul = up;
-                        e.out_act = TT; e.ld_act = C; e.act_slope = 0.1f;
-                        TTSB_PROPAGATE(conv_forward(h->c1[idx], rt, p == 0 ? LX0 : LXA, C, bc, rows, e, stream));
+                        e.out_act = TT; e.ld_act = C; e.act_slope = kSlope;
+                        TTSB_PROPAGATE(conv_forward(h->c1[idx], rt, act_chain ? lx_in : (p == 0 ? LX0 : LXA), C, bc, rows, e, stream));
                     }
                     EpiParams e;
                     e.lens = lens; e.len_mul = up;
-                    e.residual = p == 0 ? X0 : XA; e.ld_res = C;
+                    if (act_chain) {
+                        e.residual = lx_in; e.ld_res = C; e.res_inv = 1.f / kSlope;
+                    } else {
+                        e.residual = p == 0 ? X0 : XA; e.ld_res = C;
+                    }
                     if (p < 2) {
-                        e.out_raw = fused && p == 1 ? XB : XA; e.ld_raw = C;
-                        if (!fused) { e.out_act = LXA; e.ld_act = C; }
-                        e.act_slope = 0.1f;
+                        if (act_chain) {
+                            e.out_act = p == 0 ? LXA : LXB; e.ld_act = C;
+                        } else {
+                            e.out_raw = fused && p == 1 ? XB : XA; e.ld_raw = C;
+                            if (!fused) { e.out_act = LXA; e.ld_act = C; }
+                        }
+                        e.act_slope = kSlope;
                     } else {
                         e.mrf_buf = XS;
                         e.mrf_scale = 1.f / static_cast<float>(cfg.num_kernels);
@@ -312,8 +340,9 @@ int ttsb_hifigan_forward(ttsb_hifigan_t* h, const float* d_mel_f32, const void* 
                         }
                     }
                     if (fused) {
-                        const __half* xin = p == 0 ? X0 : (p == 1 ? XA : XB);
-                        TTSB_PROPAGATE(conv_pair_forward(h->c1[idx], h->c2[idx], h->pair[idx], rt, xin, bc, rows, 0.1f, e, stream));
+                        const __half* xin = act_chain ? lx_in : (p == 0 ? X0 : (p == 1 ? XA : XB));
+                        TTSB_PROPAGATE(conv_pair_forward(h->c1[idx], h->c2[idx], h->pair[idx], rt, xin, bc, rows, kSlope, e, stream,
+                                                         act_chain ? 1 : 0));
                     } else {
                         TTSB_PROPAGATE(conv_forward(h->c2[idx], rt, TT, C, bc, rows, e, stream));
                     }
@@ -326,6 +355,7 @@ int ttsb_hifigan_forward(ttsb_hifigan_t* h, const float* d_mel_f32, const void* 
                                              d_wav + static_cast<size_t>(b0) * T * h->hop, stream));
     }
     return 0;
+    });
 }
 
 }  // extern "C"

@@ -405,11 +405,11 @@ int launch_attention(const __half* qkv, const int* lens, int B, int S, float sca
         TTSB_CHECK_CUDA(cudaGetLastError());
         return 0;
     }
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (!configured.here()) {
         TTSB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              kAttSmem));
-        configured = true;
+        configured.here() = true;
     }
     attention_kernel<<<grid, 256, kAttSmem, s>>>(qkv, lens, S, scale, out);
     count_launch();

@@ -14,9 +14,10 @@ struct GlobalRuntime {
     int impl = IMPL_TC;
     int tc_version = 2;
     int desc_mode = 0;  // verified on B200 (profiles/r01_s1_probe_conv.json): base_offset stays 0
-    int* err_flag = nullptr;
-    float* simt_scratch = nullptr;
-    size_t simt_scratch_elems = 0;
+    // per device (a handle on cuda:1 must not be handed cuda:0's flag / scratch)
+    int* err_flag[kMaxDevices] = {};
+    float* simt_scratch[kMaxDevices] = {};
+    size_t simt_scratch_elems[kMaxDevices] = {};
     long long* timeline = nullptr;
 };
 GlobalRuntime& global_runtime();

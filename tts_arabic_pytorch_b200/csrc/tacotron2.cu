@@ -426,10 +426,12 @@ T2State carve_t2(const ttsb_tacotron2* h, void* p, int B, int L, int max_steps, 
 extern "C" {
 
 int ttsb_tacotron2_create(const ttsb_tensor_t* weights, int n_weights, int device, ttsb_tacotron2_t** out) {
+    return guarded_call([&]() -> int {
     TTSB_REQUIRE(weights && out, "null argument");
-    TTSB_CHECK_CUDA(cudaSetDevice(device));
+    TTSB_DEVICE_GUARD(device);
     TensorTable tab(weights, n_weights);
-    ttsb_tacotron2* h = new ttsb_tacotron2();
+    std::unique_ptr<ttsb_tacotron2, void (*)(ttsb_tacotron2*)> owner(new ttsb_tacotron2(), ttsb_tacotron2_destroy);
+    ttsb_tacotron2* h = owner.get();
     h->device = device;
     TTSB_GET_TENSOR(emb, tab, "embedding.weight", 2);
     h->n_symbol = static_cast<int>(emb->shape[0]);
@@ -519,8 +521,9 @@ int ttsb_tacotron2_create(const ttsb_tensor_t* weights, int n_weights, int devic
     for (int i = 0; i < 5; ++i)
         TTSB_PROPAGATE(make_conv_bn_layer(h->post[i], tab, "postnet.convolutions." + std::to_string(i), dims[i + 1], dims[i], 5,
                                           i == 0 ? h->mel_ld : 512, i == 4 ? h->mel_ld : 512));
-    *out = h;
+    *out = owner.release();
     return 0;
+    });
 }
 
 void ttsb_tacotron2_destroy(ttsb_tacotron2_t* h) {
@@ -549,10 +552,12 @@ size_t ttsb_tacotron2_workspace_bytes(const ttsb_tacotron2_t* h, int B, int L, i
 int ttsb_tacotron2_encode(ttsb_tacotron2_t* h, const int64_t* d_tokens, const int32_t* d_lengths,
                           const int64_t* d_speaker_ids, int B, int L, int max_steps, void* d_state, void* d_workspace,
                           size_t workspace_bytes, void* stream_) {
+    return guarded_call([&]() -> int {
     TTSB_REQUIRE(h && d_tokens && d_lengths && d_state && d_workspace, "null argument");
     TTSB_REQUIRE(B > 0 && B <= 64 && L > 0 && max_steps > 0, "batch must be 1..64");
     TTSB_REQUIRE(h->spk_emb == nullptr || d_speaker_ids != nullptr, "speaker ids required for a multi-speaker model");
     TTSB_REQUIRE(workspace_bytes >= ttsb_tacotron2_workspace_bytes(h, B, L, 0), "workspace too small");
+    TTSB_DEVICE_GUARD(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream_);
     ConvRuntime rt;
     TTSB_PROPAGATE(get_conv_runtime(static_cast<size_t>(B) * L * 2048, rt));
@@ -598,6 +603,7 @@ int ttsb_tacotron2_encode(ttsb_tacotron2_t* h, const int64_t* d_tokens, const in
     TTSB_CHECK_CUDA(cudaMemsetAsync(st.done_step, 0xFF, 4 * sizeof(int), s));
     TTSB_CHECK_CUDA(cudaGetLastError());
     return 0;
+    });
 }
 
 /* Runs decoder steps [step0, step0 + n_steps). d_masks: [n_steps, 2, B, P] bytes (1 = keep) for the
@@ -605,8 +611,10 @@ int ttsb_tacotron2_encode(ttsb_tacotron2_t* h, const int64_t* d_tokens, const in
  * step index at which every utterance had finished, or -1. */
 int ttsb_tacotron2_decode(ttsb_tacotron2_t* h, int B, int L, int max_steps, int step0, int n_steps,
                           const uint8_t* d_masks, float gate_threshold, void* d_state, int* h_done_step, void* stream_) {
+    return guarded_call([&]() -> int {
     TTSB_REQUIRE(h && d_masks && d_state, "null argument");
     TTSB_REQUIRE(step0 >= 0 && n_steps > 0 && step0 + n_steps <= max_steps, "step range");
+    TTSB_DEVICE_GUARD(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream_);
     T2State st = carve_t2(h, d_state, B, L, max_steps, nullptr);
     const int H = h->H, M = h->M, P = h->P;
@@ -635,6 +643,7 @@ int ttsb_tacotron2_decode(ttsb_tacotron2_t* h, int B, int L, int max_steps, int 
         TTSB_CHECK_CUDA(cudaStreamSynchronize(s));
     }
     return 0;
+    });
 }
 
 /* After decoding T steps: postnet + residual -> d_mel [B, n_mel, T] fp32, d_mel_lengths [B] int32,
@@ -642,9 +651,11 @@ int ttsb_tacotron2_decode(ttsb_tacotron2_t* h, int B, int L, int max_steps, int 
 int ttsb_tacotron2_finish(ttsb_tacotron2_t* h, int B, int L, int max_steps, int T, float* d_mel, int32_t* d_mel_lengths,
                           float* d_alignments, void* d_mel_cl, void* d_state, void* d_workspace, size_t workspace_bytes,
                           void* stream_) {
+    return guarded_call([&]() -> int {
     TTSB_REQUIRE(h && d_mel && d_mel_lengths && d_state && d_workspace, "null argument");
     TTSB_REQUIRE(T > 0 && T <= max_steps, "T out of range");
     TTSB_REQUIRE(workspace_bytes >= ttsb_tacotron2_workspace_bytes(h, B, L, T), "workspace too small");
+    TTSB_DEVICE_GUARD(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream_);
     ConvRuntime rt;
     TTSB_PROPAGATE(get_conv_runtime(static_cast<size_t>(B) * T * 512, rt));
@@ -684,6 +695,7 @@ int ttsb_tacotron2_finish(ttsb_tacotron2_t* h, int B, int L, int max_steps, int 
     }
     TTSB_CHECK_CUDA(cudaGetLastError());
     return 0;
+    });
 }
 
 }  // extern "C"
