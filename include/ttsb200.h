@@ -125,18 +125,27 @@ size_t ttsb_fastpitch_state_bytes(const ttsb_fastpitch_t* h, int B, int L);
 size_t ttsb_fastpitch_workspace_bytes(const ttsb_fastpitch_t* h, int B, int L, int T);
 
 /* d_ids [B,L] int64 (0 = padding, trailing only). Outputs: d_log_dur [B,L] fp32 (masked head
- * output, before exp), d_pitch [B,L] fp32. speaker < 0 = no speaker embedding. */
+ * output, before exp), d_pitch [B,L] fp32. Speaker conditioning (model.py:358-362, multi-speaker checkpoints only):
+ * d_speaker_ids [B] int64 per utterance, or NULL and one `speaker` for the whole batch; speaker < 0 with NULL ids = none.
+ * Ids are validated ON THE DEVICE (no host sync here): out-of-range token / speaker ids and non-trailing padding are
+ * reported through ttsb_fastpitch_condition's d_summary[1]; the gathers themselves are clamped. */
 int ttsb_fastpitch_encode(ttsb_fastpitch_t* h, const int64_t* d_ids, int B, int L, int speaker,
-                          float* d_log_dur, float* d_pitch, void* d_state, void* d_workspace,
-                          size_t workspace_bytes, void* stream);
+                          const int64_t* d_speaker_ids, float* d_log_dur, float* d_pitch, void* d_state,
+                          void* d_workspace, size_t workspace_bytes, void* stream);
+/* Tap for parity tests: after encode (and before condition, which adds the pitch / energy embeddings in place) the state
+ * holds the encoder output enc_out [B,L,d_model] as fp16 (model.py:364, `enc_out, enc_mask = self.encoder(...)`). */
+int ttsb_fastpitch_read_enc_out(ttsb_fastpitch_t* h, int B, int L, const void* d_state, void* d_enc_out, void* stream);
 /* d_pitch_in [B,L]: pitch track to embed (predicted, transformed or target). d_energy_tgt [B,L] or
  * NULL (predict). d_dur_tgt [B,L] or NULL (use exp(log_dur)-1). Outputs: d_dur_pred [B,L],
- * d_energy_pred [B,L] (untouched if no energy conditioning), d_dec_lens [B] int64. */
+ * d_energy_pred [B,L] (untouched if no energy conditioning), d_dec_lens [B] int64, and d_summary (int32[2], may be
+ * NULL): [0] = max(dec_lens) — the one value the caller has to read on the host before decode (the reference's own
+ * sync, model.py:76) — and [1] = input status bits from encode: 1 token id outside [0, n_symbols), 2 padding that is
+ * not trailing or an empty utterance, 4 speaker id outside [0, n_speakers). */
 int ttsb_fastpitch_condition(ttsb_fastpitch_t* h, int B, int L, const float* d_log_dur,
                              const float* d_pitch_in, const float* d_energy_tgt, const float* d_dur_tgt,
                              float pace, float max_duration, float* d_dur_pred, float* d_energy_pred,
-                             int64_t* d_dec_lens, void* d_state, void* d_workspace, size_t workspace_bytes,
-                             void* stream);
+                             int64_t* d_dec_lens, int32_t* d_summary, void* d_state, void* d_workspace,
+                             size_t workspace_bytes, void* stream);
 /* T = max(dec_lens) read by the caller. d_mel [B,n_mel,T] fp32 (reference layout; frames beyond
  * an utterance hold proj.bias exactly like the reference). d_mel_cl optional [B,T,128] fp16
  * channel-last copy for ttsb_hifigan_forward (zero beyond each utterance), may be NULL. */

@@ -61,7 +61,7 @@ def generator_layers(frames):
         # the up-sampler reads rows/stride input rows of c_in channels
         stride = 8 if s < 2 else 2
         up = layer('ups%d %d->%d' % (s, c_in, c), rows, c_in, c, up_taps[s])
-        up['hbm'] = (rows / stride * c_in + rows * c * (2 if c > 64 else 1)) * 2 / HBM
+        up['hbm'] = (rows / stride * c_in + rows * c * (1 if ACT_CHAIN else (2 if c > 64 else 1))) * 2 / HBM
         out.append(up)
         for k in (3, 7, 11):
             for j, d in enumerate((1, 3, 5)):
@@ -69,9 +69,10 @@ def generator_layers(frames):
                 mrf = rows * c * 2 * (1 if k == 3 else 2) if last else 0      # MRF accumulator: write (k=3) / read + write
                 if c > 64:
                     out.append(layer('s%d C%d k%d d%d conv1' % (s, c, k, d), rows, c, c, k))
-                    # conv2 reads the residual and writes the raw sum and its leaky-relu
+                    # conv2 reads the residual and writes the sum: once, activated, in the round-2 data flow
+                    # (csrc/hifigan.cu); round 1 wrote the raw sum AND its leaky-relu
                     out.append(layer('s%d C%d k%d d1 conv2' % (s, c, k), rows, c, c, k,
-                                     extra_rw=rows * c * 2 * 2 + mrf))
+                                     extra_rw=rows * c * 2 * (1 if ACT_CHAIN else 2) + mrf))
                 else:
                     out.append(layer('s%d C%d k%d d%d pair' % (s, c, k, d), rows, c, c, k, extra_rw=mrf,
                                      resident=True, fused=2))
@@ -80,12 +81,27 @@ def generator_layers(frames):
     return out
 
 
+ACT_CHAIN = True     # round-2 data flow; pass a third argument `r1` for round-1 launch lists
+
+
 def main():
+    global ACT_CHAIN
     path, frames = sys.argv[1], int(sys.argv[2])
+    if len(sys.argv) > 3 and sys.argv[3] == 'r1':
+        ACT_CHAIN = False
     rows = [r for r in csv.reader(l for l in open(path) if l.startswith('"'))][1:]
     durs = [(re.sub(r'\(.*', '', r[4]).replace('void ttsb::', '').replace('ttsb::', ''),
              float(r[-1].replace(',', '')) * 1e-9) for r in rows]
+    # align on the generator's own launch train: [pack_mel,] conv_pre ... conv_post_tanh (tools/run_vocoder.py
+    # --profile-last captures exactly one pass)
+    post = [i for i, (n, _) in enumerate(durs) if n.startswith('conv_post_tanh')]
     layers = generator_layers(frames)
+    if post:
+        first = post[-1] - len(layers) + 1
+        if first < 0:           # the capture began after the pass did: keep the launches it has, right-aligned
+            layers = layers[-first:]
+            first = 0
+        durs = durs[first:post[-1] + 1]
     durs = durs[:len(layers)]
     print('generator launches of one %d-frame chunk: measured (ncu, serialised) vs floors at %.2f GHz' % (frames, CLK / 1e9))
     print('%-28s %-24s %8s %8s %8s %7s %8s %7s  %s' % ('layer', 'kernel', 'meas us', 'mma us', 'hbm us', 'x floor',

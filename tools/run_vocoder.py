@@ -15,6 +15,7 @@ def main():
     ap.add_argument('--batch', type=int, default=64)
     ap.add_argument('--frames', type=int, default=512)
     ap.add_argument('--reps', type=int, default=3)
+    ap.add_argument('--profile-last', action='store_true', help='cudaProfilerStart/Stop around the last pass (ncu --profile-from-start off)')
     a = ap.parse_args()
     import torch
     from tts_arabic_pytorch_b200 import _lib
@@ -33,10 +34,15 @@ def main():
     for i in range(a.reps):
         n0 = lib.ttsb_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if a.profile_last and i == a.reps - 1:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
         e0.record()
         wav = voc(mel)
         e1.record()
         torch.cuda.synchronize()
+        if a.profile_last and i == a.reps - 1:
+            torch.cuda.profiler.stop()
         times.append(e0.elapsed_time(e1))
         launches = lib.ttsb_launch_count() - n0
     fl = 614.1e6 * a.batch * a.frames

@@ -55,7 +55,9 @@ def main():
                 v = [int(row[8 + i * 8 + k]) - base if int(row[8 + i * 8 + k]) > 0 else -1 for k in range(8)]
                 print('    tile %d  mma %6d %6d %6d | epi %6d %6d %6d %6d | panel %6d' % (i, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]))
                 d = [int(row[64 + i * 8 + k]) - base if int(row[64 + i * 8 + k]) > 0 else -1 for k in range(7)]
-                print('            epi detail: seen %d res_row %d acc_loaded %d drained %d math %d raw_stored %d act_stored %d' % tuple(d))
+                w = int(row[64 + i * 8 + 7])
+                print('            epi detail (lean: seen, chunk 0 res_rows / acc_loaded / math / stored, end): %s | issuer waited %d cycles in %d of the weight stages'
+                      % (' '.join('%d' % a for a in d), w // 1000, w % 1000))
 
 
 if __name__ == '__main__':

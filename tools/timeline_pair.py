@@ -8,7 +8,7 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 
 NAMES = ['x_issue', 'x_land', 'xform', 'c1_rdy', 'c1_iss', 'c2_rdy', 'c2_iss', 'acc1', 'tt_free', 'mid_done',
-         'fin_wait', 'acc2', 'fin_done']
+         'fin_wait', 'acc2', 'fin_done', 'mid_ld0', 'mid_sts', 'mid_fnc']
 
 
 def main():
@@ -50,8 +50,10 @@ def main():
         base = int(row[0])
         print('cta %3d' % cta)
         for i in range(7):
-            v = [int(row[8 + i * 16 + j]) - base if int(row[8 + i * 16 + j]) > 0 else -1 for j in range(13)]
+            v = [int(row[8 + i * 16 + j]) - base if int(row[8 + i * 16 + j]) > 0 else -1 for j in range(16)]
             print('  item %d  ' % i + ' '.join('%8d' % a for a in v))
+        d = [int(row[120 + j]) - base if int(row[120 + j]) > 0 else -1 for j in range(6)]
+        print('  final epilogue of item 4: acc seen %d, chunk 0: residual rows %d, acc loaded %d, math %d, stored %d; end %d' % tuple(d))
 
 
 if __name__ == '__main__':

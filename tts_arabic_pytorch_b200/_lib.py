@@ -9,7 +9,9 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libttsb200.so')
+# TTSB_LIB: an alternative build of the same C ABI (tools/build_variant.py builds one from any git ref) for same-box A/B
+# measurements — boxes differ by a few per cent, so two kernels are only comparable inside one GPU session
+LIB_PATH = os.environ.get('TTSB_LIB') or os.path.join(_HERE, 'libttsb200.so')
 _lock = threading.Lock()
 _lib = None
 
@@ -57,10 +59,11 @@ _SIGNATURES = {
     'ttsb_fastpitch_destroy': (None, [c_void_p]),
     'ttsb_fastpitch_state_bytes': (c_size_t, [c_void_p, c_int, c_int]),
     'ttsb_fastpitch_workspace_bytes': (c_size_t, [c_void_p, c_int, c_int, c_int]),
-    'ttsb_fastpitch_encode': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+    'ttsb_fastpitch_encode': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_size_t, c_void_p]),
+    'ttsb_fastpitch_read_enc_out': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'ttsb_fastpitch_condition': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
-                                         c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                         c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                          c_void_p]),
     'ttsb_fastpitch_decode': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_size_t, c_void_p]),

@@ -106,6 +106,7 @@ int ttsb_conv1d_forward(ttsb_conv1d_t* h, const void* d_in, int B, int T, const 
                         float act_slope, const int32_t* d_lens, void* d_out, void* stream) {
     return guarded_call([&]() -> int {
     TTSB_REQUIRE(h && d_in && d_out, "null argument");
+    TTSB_REQUIRE(act_slope <= 1.f, "leaky-relu slope must be <= 1 (the epilogue evaluates it as max(x, slope * x))");
     TTSB_DEVICE_GUARD(h->device);
     ConvRuntime rt;
     TTSB_PROPAGATE(get_conv_runtime(static_cast<size_t>(B) * T * h->layer.n_total, rt));

@@ -44,7 +44,7 @@ struct ConvPairArgs {
     int tt_rows;      // TT panel rows per chunk (multiple of 8, >= 128 + 2*h2)
     int x_slots, tt_slots;
     int w2_resident, b_stages;
-    int stage2;       // 1: a second set of 8 x 2 KB staging tiles (residual transposes) follows the bias tile (run_epilogue_lean)
+    int smem_res;     // 1: kernel instantiated with kSmemRes (host-side record; see conv_pair_forward)
     int in_act;       // 1: x is stored activated (lrelu(x)): the TMA panel IS conv1's operand — no in-place transform, the conv1
                       // issuer waits for the panel itself; the final epilogue recovers x for the residual (EpiParams::res_inv)
     const __half* w1;
@@ -103,7 +103,9 @@ __device__ __forceinline__ void pair_transform_slot(const ConvPairArgs& args, ui
     if (tid == 0) tlp_mark(args, item, 2);
 }
 
-template <int kTmemCols, int kEpi>
+// kSmemRes: the final epilogue takes its residual rows from the x panel in shared memory (activated chain, deep x ring;
+// see run_epilogue_lean) and releases the panel itself: x_empty then counts conv1's commit + the 4 final-epilogue warps.
+template <int kTmemCols, int kEpi, bool kSmemRes>
 __global__ void __launch_bounds__(kPairThreads, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ ConvPairArgs args) {
     constexpr int kKSteps = kTmemCols == 128 ? 2 : 4;
@@ -150,7 +152,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     if (warp == 0 && elect_one()) {
         if (args.timeline != nullptr && blockIdx.x < 256) args.timeline[blockIdx.x * 128] = clock64();
         tma_prefetch_desc(&tmap_x);
-        for (int i = 0; i < args.x_slots; ++i) { mbar_init(&x_full[i], 1); mbar_init(&xl_full[i], kPairXformWarps); mbar_init(&x_empty[i], 1); }
+        for (int i = 0; i < args.x_slots; ++i) { mbar_init(&x_full[i], 1); mbar_init(&xl_full[i], kPairXformWarps); mbar_init(&x_empty[i], kSmemRes ? 5 : 1); }
         for (int i = 0; i < args.b_stages; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tt_full[i], 4); mbar_init(&tt_empty[i], 1);
@@ -366,14 +368,21 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
             for (int ci = 0; ci < kC / 32; ++ci) {
                 const int c0 = ci * 32;
+                // this chunk's bias values are requested before the accumulator load is waited for (bias8s_early)
+                float bs_nxt[8];
+                bias8s_early(sb1 + c0 * 4, bs_nxt);
                 tmem_ld_wait(v[ci & 1]);
+                if (ci == 0 && m == 0) tlp_mark(args, it, 13);
                 if (ci + 1 < kC / 32) tmem_ld32_issue(taddr + c0 + 32, v[(ci + 1) & 1]);
-                const int chunk = c0 / args.chunk_k;
-                const int u0 = (c0 - chunk * args.chunk_k) >> 3;
+                constexpr int kChunkK = kTmemCols == 128 ? 32 : 64;
+                const int chunk = c0 / kChunkK;
+                const int u0 = (c0 - chunk * kChunkK) >> 3;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
-                    float bs[8], a[8];
-                    bias8s(sb1 + (c0 + g * 8) * 4, bs);
+                    float a[8], bs[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) bs[j] = bs_nxt[j];
+                    if (g < 3) bias8s_early(sb1 + (c0 + (g + 1) * 8) * 4, bs_nxt);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float y = v[ci & 1][g * 8 + j] + bs[j];
@@ -382,9 +391,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     if (!(args.debug & 2)) sts128(tt_base + chunk * ttp_bytes + ((u0 + g) ^ phase) * 16, pack8(a));
                 }
             }
+            if (m == 0) tlp_mark(args, it, 14);
             tc_fence_before();
             fence_proxy_async();
             __syncwarp();
+            if (m == 0) tlp_mark(args, it, 15);
             if (elect_one()) {
                 mbar_arrive(&acc1_empty[b1]);
                 mbar_arrive(&tt_full[st]);
@@ -401,19 +412,30 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const int q = warp & 3;
         constexpr bool kMrf = kEpi == 2;
         uint8_t* stage = smem_stage + (warp - 8) * 2048;
-        uint8_t* stage_in = args.stage2 ? smem_stage + 8 * 2048 + 1024 + (warp - 8) * 2048 : nullptr;
         const int b2 = g;
         uint32_t par = 0;
         LeanPrefetch<kMrf> pre_cur, pre_nxt;
         const int idx_first = blockIdx.x + g * grid;
+        // kSmemRes: only lens[b] travels a tile ahead (the residual rows come from shared memory)
+        auto prefetch = [&](const RowIO& io, long row0, bool on, LeanPrefetch<kMrf>& p, int b) {
+            if (kSmemRes) p.len_rows = (on && args.epi.lens != nullptr) ? __ldg(args.epi.lens + b) * args.epi.len_mul : 0x7fffffff;
+            else lean_prefetch(args.epi, io, row0, 0, on, p, b);
+        };
         if (idx_first < args.n_work) {
             const int b0 = idx_first / args.tiles_t;
             const int t00 = (idx_first - b0 * args.tiles_t) * args.m_out;
             const int w0 = t00 + q * 32;
             RowIO io{stage, lane, min(32, max(0, min(args.T, t00 + args.m_out) - w0))};
-            lean_prefetch(args.epi, io, static_cast<long>(b0) * args.T + w0, 0, true, pre_cur, b0);
+            prefetch(io, static_cast<long>(b0) * args.T + w0, true, pre_cur, b0);
         }
         const bool tl_on = q == 0 && lane == 0;
+        int n_items = 0;
+        for (int idx = blockIdx.x; idx < args.n_work; idx += grid) ++n_items;
+        // x ring position of this group's items (it = g, g + 2, ...): slot it % x_slots, parity (it / x_slots) & 1
+        int sxr = g % args.x_slots;
+        uint32_t pxr = static_cast<uint32_t>(g / args.x_slots) & 1u;
+        const int prow = q * 32 + lane + args.h2 + h1;                 // this lane's row inside the x panel
+        const uint32_t res_phase = row_bytes == 128 ? (prow & 7) : ((prow >> 1) & 3);
         int it = g;
         for (int idx = idx_first; idx < args.n_work; idx += 2 * grid, it += 2) {
             const int b = idx / args.tiles_t;
@@ -423,6 +445,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             TmemAcc acc{tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc2_col + b2 * C};
             auto wait_acc = [&] {
                 mbar_wait(&acc2_full[b2], par, args.err_flag, 312);
+                // the panel was written by TMA and is read with ld.shared here: observe its own barrier (long complete)
+                if (kSmemRes) mbar_wait(&x_full[sxr], pxr, args.err_flag, 313);
                 tc_fence_after();
                 if (tl_on) tlp_mark(args, it, 11);
             };
@@ -437,16 +461,28 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             const int nt0 = nvalid ? (nidx - nb * args.tiles_t) * args.m_out : 0;
             const int nw0 = nt0 + q * 32;
             RowIO nio{stage, lane, min(32, max(0, min(args.T, nt0 + args.m_out) - nw0))};
+            const uint32_t res_saddr = smem_u32(smem_x + sxr * xslot_bytes) + prow * row_bytes;
+            // (detail stamps only where registers allow: the global-residual variants are at the 128-register limit)
+            long long* dbg = (kSmemRes && tl_on && it == 4 && args.timeline != nullptr && blockIdx.x < 256) ? args.timeline + blockIdx.x * 128 + 120 : nullptr;
             if (args.debug & 4) {
                 wait_acc();
                 drained();
             } else {
-                // the next tile's residual rows are requested before this tile's accumulator is waited for — except in
-                // the MRF variant, whose extra live chunks would spill (and a spill reload is an L2 round trip here)
-                if (!kMrf) lean_prefetch(args.epi, nio, static_cast<long>(nb) * args.T + nw0, 0, nvalid, pre_nxt, nb);
-                run_epilogue_lean<kMrf, true, !kMrf>(args.epi, acc, b, t, 0, C, wait_acc, drained, stage, pre_cur, t0 + args.m_out,
-                                        smem_u32(sbias2), nullptr, nullptr, nullptr, stage_in);
-                if (kMrf) lean_prefetch(args.epi, nio, static_cast<long>(nb) * args.T + nw0, 0, nvalid, pre_nxt, nb);
+                // The next tile's residual rows are requested right AFTER this tile's epilogue (they are in flight while the
+                // next accumulator is waited for), not before it: 16 more live registers during the epilogue spill at the
+                // 128-register budget, and a spilled load result is waited for on the spot (an L2 round trip per item).
+                // Shared-memory residual: only lens[b] is fetched, a tile ahead.
+                if (kSmemRes) prefetch(nio, static_cast<long>(nb) * args.T + nw0, nvalid, pre_nxt, nb);
+                run_epilogue_lean<kMrf, true, !kMrf, kSmemRes, kSmemRes>(args.epi, acc, b, t, 0, C, wait_acc, drained, stage, pre_cur,
+                                        t0 + args.m_out, smem_u32(sbias2), nullptr, nullptr, nullptr, nullptr, dbg, res_saddr, res_phase);
+                if (!kSmemRes) prefetch(nio, static_cast<long>(nb) * args.T + nw0, nvalid, pre_nxt, nb);
+            }
+            if (kSmemRes) {
+                // every residual read of this warp is done (ld.shared results were consumed above): release the panel
+                __syncwarp();
+                if (elect_one()) mbar_arrive(&x_empty[sxr]);
+                sxr += 2;
+                if (sxr >= args.x_slots) { sxr -= args.x_slots; pxr ^= 1u; }
             }
             pre_cur = pre_nxt;
             if (tl_on) tlp_mark(args, it, 12);
@@ -514,18 +550,25 @@ ConvPairPlan conv_pair_plan(const ConvLayer& L1, const ConvLayer& L2) {
     return p;
 }
 
-template <int kCols, int kEpi>
-static int launch_pair(const CUtensorMap& tm, const ConvPairArgs& a, int grid, size_t smem, cudaStream_t s) {
+template <int kCols, int kEpi, bool kSmemRes>
+static int launch_pair_impl(const CUtensorMap& tm, const ConvPairArgs& a, int grid, size_t smem, cudaStream_t s) {
     static PerDeviceOnce configured;
     if (!configured.here()) {
-        TTSB_CHECK_CUDA(cudaFuncSetAttribute(conv_pair_kernel<kCols, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        TTSB_CHECK_CUDA(cudaFuncSetAttribute(conv_pair_kernel<kCols, kEpi, kSmemRes>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(kPairSmemMax)));
         configured.here() = true;
     }
-    conv_pair_kernel<kCols, kEpi><<<grid, kPairThreads, smem, s>>>(tm, a);
+    conv_pair_kernel<kCols, kEpi, kSmemRes><<<grid, kPairThreads, smem, s>>>(tm, a);
     count_launch();
     TTSB_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+template <int kCols>
+static int launch_pair(const CUtensorMap& tm, const ConvPairArgs& a, int grid, size_t smem, cudaStream_t s, bool mrf) {
+    if (a.smem_res)
+        return mrf ? launch_pair_impl<kCols, 2, true>(tm, a, grid, smem, s) : launch_pair_impl<kCols, 1, true>(tm, a, grid, smem, s);
+    return mrf ? launch_pair_impl<kCols, 2, false>(tm, a, grid, smem, s) : launch_pair_impl<kCols, 1, false>(tm, a, grid, smem, s);
 }
 
 int conv_pair_forward(const ConvLayer& L1, const ConvLayer& L2, const ConvPairPlan& plan, const ConvRuntime& rt,
@@ -549,9 +592,6 @@ int conv_pair_forward(const ConvLayer& L1, const ConvLayer& L2, const ConvPairPl
     a.x_slots = plan.x_slots; a.tt_slots = plan.tt_slots;
     a.w2_resident = plan.w2_resident; a.b_stages = plan.b_stages;
     a.in_act = in_act ? 1 : 0;
-    // the final epilogue's TMA-less stores still go LDS -> STG through the staging tile; a second tile set only pays with
-    // TMA output, which conv_pair does not use yet
-    a.stage2 = 0;
     a.w1 = L1.w_packed; a.w2 = L2.w_packed;
     a.bias1 = L1.bias;
     a.slope = slope;
@@ -566,15 +606,16 @@ int conv_pair_forward(const ConvLayer& L1, const ConvLayer& L2, const ConvPairPl
     epi.ld_res = plan.C;
     epi.res_inv = in_act ? 1.f / slope : 1.f;
     a.epi = epi;
+    // shared-memory residual: activated input (the panel holds what the residual add needs), one channel chunk, and an x
+    // ring deep enough to keep a panel until its item's final epilogue (producer -> conv1 -> mid -> conv2 -> final)
+    static const int want_smem_res = getenv("TTSB_PAIR_SMEM_RES") ? atoi(getenv("TTSB_PAIR_SMEM_RES")) : 1;
+    a.smem_res = (want_smem_res && in_act && L1.n_chunks == 1 && plan.x_slots >= 5) ? 1 : 0;
     const int grid = std::min(num_sms(), a.n_work);
     const bool mrf = epi.mrf_mode != MRF_NONE;
     switch (plan.tmem_cols) {
-        case 128: return mrf ? launch_pair<128, 2>(*tm, a, grid, plan.smem_bytes, stream)
-                             : launch_pair<128, 1>(*tm, a, grid, plan.smem_bytes, stream);
-        case 256: return mrf ? launch_pair<256, 2>(*tm, a, grid, plan.smem_bytes, stream)
-                             : launch_pair<256, 1>(*tm, a, grid, plan.smem_bytes, stream);
-        case 512: return mrf ? launch_pair<512, 2>(*tm, a, grid, plan.smem_bytes, stream)
-                             : launch_pair<512, 1>(*tm, a, grid, plan.smem_bytes, stream);
+        case 128: return launch_pair<128>(*tm, a, grid, plan.smem_bytes, stream, mrf);
+        case 256: return launch_pair<256>(*tm, a, grid, plan.smem_bytes, stream, mrf);
+        case 512: return launch_pair<512>(*tm, a, grid, plan.smem_bytes, stream, mrf);
     }
     TTSB_REQUIRE(false, "bad tmem_cols for conv pair");
     return 1;

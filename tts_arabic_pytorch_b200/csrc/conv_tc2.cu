@@ -222,6 +222,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     // address) and, in mode 2, the barrier of the NEXT weight stage is tested before this stage's MMAs are
                     // issued, which takes the barrier read off the per-stage dependent chain.
                     const uint64_t hi = static_cast<uint64_t>(desc_hi) << 32;
+                    long long wait_b = 0, wait_n = 0;   // debug timeline: cycles / stages this tile waited for weight tiles
                     for (int c = 0; c < args.n_chunks; ++c) {
                         mbar_wait(&full_a[sa], pa, args.err_flag, 204);
                         uint32_t al = ((a_lo0 + sa * panel_u) & 0x3FFFu) | lo_flag;
@@ -235,7 +236,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                             if (args.resident) {
                                 bl = ((b_lo0 + (c * args.n_taps + tap) * btile_u) & 0x3FFFu) | lo_flag;
                             } else {
-                                if (!b_ready) mbar_wait(&full_b[sb], pb, args.err_flag, 205);
+                                if (!b_ready) {
+                                    const long long w0 = args.timeline != nullptr ? clock64() : 0;
+                                    mbar_wait(&full_b[sb], pb, args.err_flag, 205);
+                                    if (args.timeline != nullptr) { wait_b += clock64() - w0; ++wait_n; }
+                                }
                                 tc_fence_after();
                                 bl = ((b_lo0 + sb * btile_u) & 0x3FFFu) | lo_flag;
                                 cur = sb;
@@ -258,6 +263,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     }
                     umma_commit(&tmem_full[buf]);
                     if (tl_i < 7) tl2_mark(args, 8 + tl_i * 8 + 2);
+                    if (args.timeline != nullptr && blockIdx.x < 256 && tl_i < 7)
+                        args.timeline[blockIdx.x * 128 + 64 + tl_i * 8 + 7] = wait_b * 1000 + wait_n;
                     if (args.acc_bufs == 2) buf ^= 1;
                     continue;
                 }
@@ -377,9 +384,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                                      (last_r ? 0 : r + 1)) * kTileM + q * 32;
                     RowIO nio{stage, lane, min(32, max(0, args.T - nw0))};
                     lean_prefetch(args.epi, nio, static_cast<long>(nb) * args.T + nw0, n_base, nvalid, pre_nxt, nb);
+                    long long* dbg = (tl_on && args.timeline != nullptr && blockIdx.x < 256 && tl_i < 7)
+                                         ? args.timeline + blockIdx.x * 128 + 64 + tl_i * 8 : nullptr;
                     run_epilogue_lean<kMrf, true, !(kMrf && kMinBlocks >= 2)>(args.epi, acc, b, t, n_base, args.n_tile, wait_acc, drained, stage, pre_cur,
                                             0x7fffffff, smem_u32(sbias), (args.tma_out & 1) ? &tmap_raw : nullptr,
-                                            (args.tma_out & 2) ? &tmap_act : nullptr, (args.tma_out & 4) ? &tmap_mrf : nullptr, stage_in);
+                                            (args.tma_out & 2) ? &tmap_act : nullptr, (args.tma_out & 4) ? &tmap_mrf : nullptr, stage_in, dbg);
                     pre_cur = pre_nxt;
                 } else {
                     long long* dbg = (tl_on && args.timeline != nullptr && blockIdx.x < 256 && tl_i < 7)

@@ -211,6 +211,13 @@ __device__ __forceinline__ void bias8(const float* bias, int n, float (&f)[8]) {
 
 // same from shared memory (a broadcast read): with ~all of the SM's L1 carved out as shared memory the __ldg path
 // above misses to L2 — one ~700-cycle round trip per 8 columns, on the epilogue's critical path
+// volatile form: stays where it is written relative to the other volatile asm statements (tcgen05.ld, st.shared), so a
+// chunk's bias values can be requested BEFORE the accumulator load is waited for instead of right before their use
+// (each LDS -> FADD pair there is a ~30-cycle stall of a warp that has no other work; round-2 SASS review)
+__device__ __forceinline__ void bias8s_early(uint32_t saddr, float* f) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]) : "r"(saddr));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7]) : "r"(saddr + 16));
+}
 __device__ __forceinline__ void bias8s(uint32_t saddr, float (&f)[8]) {
     // not volatile: the bias tile is written once before the role dispatch, so the compiler may hoist / batch these
     asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]) : "r"(saddr));
@@ -405,13 +412,21 @@ __device__ __forceinline__ void lean_prefetch(const EpiParams& e, const RowIO& i
 // kMrf = false: mrf_mode == MRF_NONE is guaranteed by the caller.
 // kLookahead = false (register-starved variants): a chunk's residual / MRF rows are requested when the chunk
 // starts, not one chunk ahead.
-template <bool kMrf, bool kSmemBias = false, bool kLookahead = true, class Acc, class WaitFn, class DrainFn>
+template <bool kMrf, bool kSmemBias = false, bool kLookahead = true, bool kEarlyBias = true, bool kSmemRes = false, class Acc,
+          class WaitFn, class DrainFn>
 __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc& acc, int b, int t, int n_base,
                                                   int n_tile, WaitFn wait_acc, DrainFn acc_drained, uint8_t* stage,
                                                   const LeanPrefetch<kMrf>& pre, int t_end = 0x7fffffff,
                                                   uint32_t bias_saddr = 0, const CUtensorMap* tm_raw = nullptr,
                                                   const CUtensorMap* tm_act = nullptr, const CUtensorMap* tm_mrf = nullptr,
-                                                  uint8_t* stage_in = nullptr) {
+                                                  uint8_t* stage_in = nullptr, long long* dbg = nullptr,
+                                                  uint32_t res_saddr = 0, uint32_t res_phase = 0) {
+    // kSmemRes: the residual rows of this tile are still in shared memory (conv_pair: the x panel that fed conv1, in the
+    // UMMA K-major swizzled layout). res_saddr = shared address of this lane's row, res_phase = its 16-byte-unit XOR
+    // pattern; 16-byte unit u of the row sits at res_saddr + ((u ^ res_phase) << 4). No global loads, no transposes and
+    // none of the 32 prefetch registers of the global path.
+    // dbg (timeline tools): clock64() after 0 accumulator seen, then for the FIRST chunk 1 residual rows in registers,
+    // 2 accumulator chunk loaded, 3 math + pack done, 4 stores issued; 5 after the last chunk
     // stage_in: a second 2 KB tile of this warp for the residual / MRF row transposes. With ONE tile every transpose has
     // to wait until the TMA store issued just before it (the previous chunk's output) has finished reading the tile —
     // a full TMA read latency per chunk on the epilogue's critical path (round-2 timeline: ~2000 cycles per chunk).
@@ -426,7 +441,7 @@ __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc&
     RowIO io{stage, lane, min(32, max(0, min(e.T, t_end) - warp_row0))};
     RowIO io_in{stage_in != nullptr ? stage_in : stage, lane, io.rows_valid};
     const bool shared_tile = stage_in == nullptr || stage_in == stage;
-    const bool use_res = e.residual != nullptr;
+    const bool use_res = !kSmemRes && e.residual != nullptr;
     const bool use_mrf = kMrf && (e.mrf_mode == MRF_ADD || e.mrf_mode == MRF_LAST);
     const bool mrf_store = kMrf && (e.mrf_mode == MRF_FIRST || e.mrf_mode == MRF_ADD);
     const __half* res_blk = e.residual + row0 * e.ld_res + n_base;
@@ -438,6 +453,7 @@ __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc&
     Chunk32 res_cur = pre.res, mrf_cur;
     if (kMrf) io.request(mrf_blk, e.n_total, use_mrf, mrf_cur);
     wait_acc();
+    if (dbg) dbg[0] = clock64();
     // warp-uniform shortcuts: tiles without masked rows skip the selects, layers without an activated copy
     // (conv_pair steps, MRF accumulation) skip its math
     const bool any_masked = __any_sync(0xffffffffu, !in_len);
@@ -446,27 +462,52 @@ __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc&
         float v[32];
         Chunk32 res_nxt, mrf_nxt;
         const bool more = c0 + 32 < n_tile;
-        if (kLookahead) {
-            io.request(res_blk + c0 + 32, e.ld_res, use_res && more, res_nxt);
-            if (kMrf) io.request(mrf_blk + c0 + 32, e.n_total, use_mrf && more, mrf_nxt);
-        } else if (c0 > 0) {
+        const bool tma_out = tm_raw != nullptr || tm_act != nullptr || tm_mrf != nullptr;
+        if (!kLookahead && c0 > 0) {
             io.request(res_blk + c0, e.ld_res, use_res, res_cur);
             if (kMrf) io.request(mrf_blk + c0, e.n_total, use_mrf, mrf_cur);
         }
-        const bool tma_out = tm_raw != nullptr || tm_act != nullptr || tm_mrf != nullptr;
+        // The rows requested one chunk (or one tile) ago are consumed BEFORE the next request is issued: ptxas tracks both
+        // groups of loads on one scoreboard, and a request issued first made the transposes below wait for the loads that
+        // had just left (DEPBAR.LE SB0, 0 — a full L2 round trip per chunk on the critical path; round-2 timelines)
+        // (register-tight callers, kEarlyBias = false, keep the request first: the other order spills there)
+        if (kLookahead && !kEarlyBias) {
+            io.request(res_blk + c0 + 32, e.ld_res, use_res && more, res_nxt);
+            if (kMrf) io.request(mrf_blk + c0 + 32, e.n_total, use_mrf && more, mrf_nxt);
+        }
         if (use_res) io_in.to_row(res_cur, tma_out && shared_tile);
         if (kMrf && use_mrf) io_in.to_row(mrf_cur, tma_out && shared_tile);
+        if (kLookahead && kEarlyBias) {
+            io.request(res_blk + c0 + 32, e.ld_res, use_res && more, res_nxt);
+            if (kMrf) io.request(mrf_blk + c0 + 32, e.n_total, use_mrf && more, mrf_nxt);
+        }
+        // bias values travel one 8-column group ahead of their use (bias8s_early): group 0 before the accumulator load is
+        // waited for, group g + 1 while group g is computed — 8 registers more than loading at the point of use
+        // (kEarlyBias = false where that pushes a 128-register kernel into spilling: conv_pair)
+        float bs_nxt[8];
+        if (kSmemBias && kEarlyBias) bias8s_early(bias_saddr + c0 * 4, bs_nxt);
+        if (dbg && c0 == 0) dbg[1] = clock64();
         __syncwarp();
         acc.load(c0, v);
+        if (dbg && c0 == 0) dbg[2] = clock64();
         if (!more) acc_drained();
         Chunk32 o_raw, o_act;
+        const bool want_raw = mrf_store || e.out_raw != nullptr;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             float r[8], m[8], bs[8], x[8];
-            unpack8(res_cur.q[g], r);
+            if (kSmemRes) unpack8(lds128(res_saddr + ((static_cast<uint32_t>((c0 >> 3) + g) ^ res_phase) << 4)), r);
+            else unpack8(res_cur.q[g], r);
             if (kMrf) unpack8(mrf_cur.q[g], m);
-            if (kSmemBias) bias8s(bias_saddr + (c0 + g * 8) * 4, bs);
-            else bias8(e.bias, n_base + c0 + g * 8, bs);
+            if (kSmemBias && kEarlyBias) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bs[j] = bs_nxt[j];
+                if (g < 3) bias8s_early(bias_saddr + (c0 + (g + 1) * 8) * 4, bs_nxt);
+            } else if (kSmemBias) {
+                bias8s(bias_saddr + (c0 + g * 8) * 4, bs);
+            } else {
+                bias8(e.bias, n_base + c0 + g * 8, bs);
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) x[j] = v[g * 8 + j] + bs[j] + fminf(r[j], r[j] * rinv);   // rinv >= 1: inverse lrelu
             if (any_masked) {
@@ -477,14 +518,15 @@ __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc&
 #pragma unroll
                 for (int j = 0; j < 8; ++j) x[j] = m[j] + x[j] * mscale;
             }
-            o_raw.q[g] = pack8(x);
+            if (want_raw) o_raw.q[g] = pack8(x);
             if (want_act) {
                 float a[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) a[j] = x[j] > 0.f ? x[j] : x[j] * slope;
+                for (int j = 0; j < 8; ++j) a[j] = fmaxf(x[j], x[j] * slope);      // slope in [0, 1): == leaky-relu
                 o_act.q[g] = pack8(a);
             }
         }
+        if (dbg && c0 == 0) dbg[3] = clock64();
         if (mrf_store) {
             if (tm_mrf) io.store_tma(tm_mrf, n_base + c0, warp_row0, b, o_raw);
             else io.store(mrf_blk + c0, e.n_total, o_raw, tma_out);
@@ -498,11 +540,13 @@ __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc&
                 else io.store(e.out_act + row0 * e.ld_act + n_base + c0, e.ld_act, o_act, tma_out);
             }
         }
+        if (dbg && c0 == 0) dbg[4] = clock64();
         if (kLookahead) {
             res_cur = res_nxt;
             if (kMrf) mrf_cur = mrf_nxt;
         }
     }
+    if (dbg) dbg[5] = clock64();
 }
 #endif  // __CUDACC__
 

@@ -135,6 +135,7 @@ struct State {  // persistent between encode / condition / decode
     int* lens;
     int* dec_lens;
     int* cum;
+    int* summary;   // [0] max(dec_lens), [1] input status bits (launch_ids_to_lens)
     __half* x;  // [B,L,D]
 };
 struct Scratch {
@@ -147,6 +148,7 @@ State carve_state(const ttsb_fastpitch* h, void* p, int B, int L, size_t* bytes)
     s.lens = c.take<int>(B);
     s.dec_lens = c.take<int>(B);
     s.cum = c.take<int>(static_cast<size_t>(B) * (L + 1));
+    s.summary = c.take<int>(4);
     s.x = c.take<__half>(static_cast<size_t>(B) * L * h->cfg.d_model);
     if (bytes) *bytes = c.off + 256;
     return s;
@@ -306,8 +308,8 @@ size_t ttsb_fastpitch_workspace_bytes(const ttsb_fastpitch_t* h, int B, int L, i
 }
 
 int ttsb_fastpitch_encode(ttsb_fastpitch_t* h, const int64_t* d_ids, int B, int L, int speaker,
-                          float* d_log_dur, float* d_pitch, void* d_state, void* d_workspace,
-                          size_t workspace_bytes, void* stream_) {
+                          const int64_t* d_speaker_ids, float* d_log_dur, float* d_pitch, void* d_state,
+                          void* d_workspace, size_t workspace_bytes, void* stream_) {
     return guarded_call([&]() -> int {
     TTSB_REQUIRE(h && d_ids && d_log_dur && d_pitch && d_state && d_workspace, "null argument");
     TTSB_REQUIRE(B > 0 && L > 0, "empty batch");
@@ -320,9 +322,12 @@ int ttsb_fastpitch_encode(ttsb_fastpitch_t* h, const int64_t* d_ids, int B, int 
     State st = carve_state(h, d_state, B, L, nullptr);
     Scratch sc = carve_scratch(h, d_workspace, B, L, nullptr);
     const int D = h->cfg.d_model;
-    const float* cond = (h->spk_table && speaker >= 0) ? h->spk_table + static_cast<size_t>(speaker) * D : nullptr;
-    TTSB_PROPAGATE(launch_ids_to_lens(d_ids, B, L, st.lens, stream));
-    TTSB_PROPAGATE(launch_embed(d_ids, h->word_emb, cond, h->inv_freq_enc, B, L, D, st.x, stream));
+    const bool use_spk = h->spk_table != nullptr && (speaker >= 0 || d_speaker_ids != nullptr);
+    TTSB_CHECK_CUDA(cudaMemsetAsync(st.summary, 0, 4 * sizeof(int), stream));
+    TTSB_PROPAGATE(launch_ids_to_lens(d_ids, B, L, h->cfg.n_symbols, use_spk ? d_speaker_ids : nullptr, h->cfg.n_speakers,
+                                      st.lens, st.summary + 1, stream));
+    TTSB_PROPAGATE(launch_embed(d_ids, h->word_emb, use_spk ? h->spk_table : nullptr, d_speaker_ids, speaker,
+                                h->cfg.n_speakers, h->inv_freq_enc, B, L, D, h->cfg.n_symbols, st.x, stream));
     for (const FftLayer& l : h->enc) TTSB_PROPAGATE(run_fft_layer(h, l, rt, st.x, st.lens, B, L, sc, stream));
     TTSB_PROPAGATE(run_predictor(h, h->dur, rt, st.x, st.lens, B, L, sc, d_log_dur, stream));
     TTSB_PROPAGATE(run_predictor(h, h->pitch, rt, st.x, st.lens, B, L, sc, d_pitch, stream));
@@ -330,11 +335,22 @@ int ttsb_fastpitch_encode(ttsb_fastpitch_t* h, const int64_t* d_ids, int B, int 
     });
 }
 
+int ttsb_fastpitch_read_enc_out(ttsb_fastpitch_t* h, int B, int L, const void* d_state, void* d_enc_out, void* stream_) {
+    return guarded_call([&]() -> int {
+    TTSB_REQUIRE(h && d_state && d_enc_out, "null argument");
+    TTSB_DEVICE_GUARD(h->device);
+    State st = carve_state(h, const_cast<void*>(d_state), B, L, nullptr);
+    TTSB_CHECK_CUDA(cudaMemcpyAsync(d_enc_out, st.x, static_cast<size_t>(B) * L * h->cfg.d_model * sizeof(__half),
+                                    cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream_)));
+    return 0;
+    });
+}
+
 int ttsb_fastpitch_condition(ttsb_fastpitch_t* h, int B, int L, const float* d_log_dur,
                              const float* d_pitch_in, const float* d_energy_tgt, const float* d_dur_tgt,
                              float pace, float max_duration, float* d_dur_pred, float* d_energy_pred,
-                             int64_t* d_dec_lens, void* d_state, void* d_workspace, size_t workspace_bytes,
-                             void* stream_) {
+                             int64_t* d_dec_lens, int32_t* d_summary, void* d_state, void* d_workspace,
+                             size_t workspace_bytes, void* stream_) {
     return guarded_call([&]() -> int {
     TTSB_REQUIRE(h && d_log_dur && d_pitch_in && d_dur_pred && d_dec_lens && d_state && d_workspace, "null argument");
     TTSB_REQUIRE(workspace_bytes >= ttsb_fastpitch_workspace_bytes(h, B, L, 0), "workspace too small");
@@ -358,8 +374,11 @@ int ttsb_fastpitch_condition(ttsb_fastpitch_t* h, int B, int L, const float* d_l
         }
         TTSB_PROPAGATE(launch_scalar_embed_add(st.x, energy, h->energy_emb.w, h->energy_emb.b, st.lens, B, L, D, 1, stream));
     }
+    TTSB_CHECK_CUDA(cudaMemsetAsync(st.summary, 0, sizeof(int), stream));     // [0] only: the input status of encode stays
     TTSB_PROPAGATE(launch_durations(d_log_dur, d_dur_tgt, pace, max_duration, B, L, d_dur_pred, st.cum,
-                                    st.dec_lens, d_dec_lens, stream));
+                                    st.dec_lens, d_dec_lens, st.summary, stream));
+    if (d_summary)
+        TTSB_CHECK_CUDA(cudaMemcpyAsync(d_summary, st.summary, 2 * sizeof(int), cudaMemcpyDeviceToDevice, stream));
     return 0;
     });
 }

@@ -17,11 +17,15 @@ int launch_conv_post_tanh(const __half* x, const float* w, float bias, const int
 
 // word embedding gather + sinusoidal positional embedding * mask + conditioning
 // (transformer.py:212-219, 34-48). ids int64 [B,L]; out fp16 [B,L,D].
-int launch_embed(const int64_t* ids, const float* emb, const float* cond, const float* inv_freq,
-                 int B, int L, int D, __half* out, cudaStream_t s);
+// speaker conditioning (model.py:358-362): spk_table [n_speakers, D] pre-scaled, row chosen per utterance by spk_ids
+// (int64 [B]) or by spk_scalar; ids / speaker ids are clamped (reported by launch_ids_to_lens).
+int launch_embed(const int64_t* ids, const float* emb, const float* spk_table, const int64_t* spk_ids, int spk_scalar,
+                 int n_speakers, const float* inv_freq, int B, int L, int D, int n_symbols, __half* out, cudaStream_t s);
 
-// count of leading non-pad ids per row (mask = ids != padding_idx, transformer.py:214)
-int launch_ids_to_lens(const int64_t* ids, int B, int L, int* lens, cudaStream_t s);
+// count of non-pad ids per row (mask = ids != padding_idx, transformer.py:214) + input validation: *status |= 1 (token
+// id out of range), 2 (padding not trailing / empty utterance), 4 (speaker id out of range)
+int launch_ids_to_lens(const int64_t* ids, int B, int L, int n_symbols, const int64_t* spk_ids, int n_speakers, int* lens,
+                       int* status, cudaStream_t s);
 
 // single-head attention with key-padding mask (transformer.py:131-146), d_head = 64.
 // qkv: [B,S,192] fp16 (q|k|v), out: [B,S,64] fp16.
@@ -37,7 +41,7 @@ int launch_scalar_embed_add(__half* x, const float* p, const float* w, const flo
 // log_dur (masked head output) or dur_tgt; writes dur_pred (fp32), cum [B,L+1] int32, dec_lens.
 int launch_durations(const float* log_dur, const float* dur_tgt, float pace, float max_duration,
                      int B, int L, float* dur_pred, int* cum, int* dec_lens, int64_t* dec_lens64,
-                     cudaStream_t s);
+                     int* max_dec_len, cudaStream_t s);
 
 // length regulator as a row gather (model.py:81-86) fused with the decoder's positional
 // embedding (transformer.py:216-219): out[b,t,:] = enc[b,tok(t),:] + posemb(t) for t < dec_len, else 0.

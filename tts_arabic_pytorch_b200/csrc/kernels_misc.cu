@@ -101,13 +101,24 @@ __device__ __forceinline__ float posemb_val(int pos, int j, int D, const float* 
     return j < half ? sinf(a) : cosf(a);
 }
 
+// ids / speaker ids are clamped into their tables here; out-of-range values are REPORTED by ids_to_lens_kernel through
+// the status word the caller reads at its one host sync (nn.Embedding raises IndexError in the reference — a silent
+// out-of-bounds gather would be garbage audio or a poisoned context)
 __global__ void embed_kernel(const int64_t* __restrict__ ids, const float* __restrict__ emb,
-                             const float* __restrict__ cond, const float* __restrict__ inv_freq,
-                             int L, int D, __half* __restrict__ out) {
+                             const float* __restrict__ spk_table, const int64_t* __restrict__ spk_ids, int spk_scalar,
+                             int n_speakers, const float* __restrict__ inv_freq,
+                             int L, int D, int n_symbols, __half* __restrict__ out) {
     const int row = blockIdx.x;  // b*L + l
     const int l = row % L;
-    const int64_t id = ids[row];
-    const bool valid = id != 0;
+    const int64_t raw = ids[row];
+    const int64_t id = raw < 0 ? 0 : (raw >= n_symbols ? n_symbols - 1 : raw);
+    const bool valid = raw != 0;
+    const float* cond = nullptr;
+    if (spk_table != nullptr) {
+        int64_t sp = spk_ids != nullptr ? spk_ids[row / L] : spk_scalar;
+        sp = sp < 0 ? 0 : (sp >= n_speakers ? n_speakers - 1 : sp);
+        cond = spk_table + sp * D;
+    }
     for (int j = threadIdx.x; j < D; j += blockDim.x) {
         float v = emb[id * D + j];
         if (valid) v += posemb_val(l, j, D, inv_freq);
@@ -116,23 +127,41 @@ __global__ void embed_kernel(const int64_t* __restrict__ ids, const float* __res
     }
 }
 
-int launch_embed(const int64_t* ids, const float* emb, const float* cond, const float* inv_freq,
-                    int B, int L, int D, __half* out, cudaStream_t s) {
-    embed_kernel<<<B * L, 128, 0, s>>>(ids, emb, cond, inv_freq, L, D, out);
+int launch_embed(const int64_t* ids, const float* emb, const float* spk_table, const int64_t* spk_ids, int spk_scalar,
+                 int n_speakers, const float* inv_freq, int B, int L, int D, int n_symbols, __half* out, cudaStream_t s) {
+    embed_kernel<<<B * L, 128, 0, s>>>(ids, emb, spk_table, spk_ids, spk_scalar, n_speakers, inv_freq, L, D, n_symbols, out);
     count_launch();
     TTSB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
-__global__ void ids_to_lens_kernel(const int64_t* __restrict__ ids, int L, int* __restrict__ lens) {
+// lens[b] = number of non-pad ids; status bits (OR-ed into *status, which the caller zeroed): 1 an id outside
+// [0, n_symbols), 2 padding that is not trailing or an empty utterance, 4 a speaker id outside [0, n_speakers)
+__global__ void ids_to_lens_kernel(const int64_t* __restrict__ ids, int L, int n_symbols,
+                                   const int64_t* __restrict__ spk_ids, int n_speakers, int* __restrict__ lens,
+                                   int* __restrict__ status) {
     const int b = blockIdx.x;
-    int cnt = 0;
-    for (int l = threadIdx.x; l < L; l += 32) cnt += ids[static_cast<size_t>(b) * L + l] != 0 ? 1 : 0;
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if (threadIdx.x == 0) lens[b] = cnt;
+    int cnt = 0, last = -1, bad = 0;
+    for (int l = threadIdx.x; l < L; l += 32) {
+        const int64_t id = ids[static_cast<size_t>(b) * L + l];
+        if (id != 0) { ++cnt; last = l; }
+        if (id < 0 || id >= n_symbols) bad |= 1;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    if (threadIdx.x == 0) {
+        lens[b] = cnt;
+        if (cnt == 0 || last != cnt - 1) bad |= 2;
+        if (spk_ids != nullptr && (spk_ids[b] < 0 || spk_ids[b] >= n_speakers)) bad |= 4;
+        if (bad && status != nullptr) atomicOr(status, bad);
+    }
 }
-int launch_ids_to_lens(const int64_t* ids, int B, int L, int* lens, cudaStream_t s) {
-    ids_to_lens_kernel<<<B, 32, 0, s>>>(ids, L, lens);
+int launch_ids_to_lens(const int64_t* ids, int B, int L, int n_symbols, const int64_t* spk_ids, int n_speakers, int* lens,
+                       int* status, cudaStream_t s) {
+    ids_to_lens_kernel<<<B, 32, 0, s>>>(ids, L, n_symbols, spk_ids, n_speakers, lens, status);
     count_launch();
     TTSB_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -449,7 +478,7 @@ int launch_scalar_embed_add(__half* x, const float* p, const float* w, const flo
 __global__ void durations_kernel(const float* __restrict__ log_dur, const float* __restrict__ dur_tgt,
                                  float pace, float max_duration, int L, float* __restrict__ dur_pred,
                                  int* __restrict__ cum, int* __restrict__ dec_lens,
-                                 int64_t* __restrict__ dec_lens64) {
+                                 int64_t* __restrict__ dec_lens64, int* __restrict__ max_dec_len) {
     const int b = blockIdx.x;
     const int lane = threadIdx.x;
     int running = 0;
@@ -480,13 +509,14 @@ __global__ void durations_kernel(const float* __restrict__ log_dur, const float*
     if (lane == 0) {
         dec_lens[b] = running;
         if (dec_lens64) dec_lens64[b] = running;
+        if (max_dec_len) atomicMax(max_dec_len, running);
     }
 }
 int launch_durations(const float* log_dur, const float* dur_tgt, float pace, float max_duration,
                      int B, int L, float* dur_pred, int* cum, int* dec_lens, int64_t* dec_lens64,
-                     cudaStream_t s) {
+                     int* max_dec_len, cudaStream_t s) {
     durations_kernel<<<B, 32, 0, s>>>(log_dur, dur_tgt, pace, max_duration, L, dur_pred, cum, dec_lens,
-                                      dec_lens64);
+                                      dec_lens64, max_dec_len);
     count_launch();
     TTSB_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -187,7 +187,7 @@ class FastPitch(nn.Module):
     # ------------------------------------------------------------------ reference API
     @torch.no_grad()
     def infer(self, inputs, pace=1.0, dur_tgt=None, pitch_tgt=None, energy_tgt=None, pitch_transform=None,
-              max_duration=75, speaker=0, return_channel_last=False):
+              max_duration=75, speaker=0, return_channel_last=False, taps=None):
         """Same contract as the reference (model.py:351-409): returns
         (mel_out [B,80,T], dec_lens [B] int64, dur_pred [B,L], pitch_pred [B,1,L], energy_pred [B,L] | None).
         With return_channel_last=True a 6th item is appended: the fp16 [B,T,128] mel for the vocoder."""
@@ -197,10 +197,22 @@ class FastPitch(nn.Module):
         lib = _lib.load()
         ids = inputs.to(device=device, dtype=torch.int64).contiguous()
         B, L = ids.shape
+        if L == 0:
+            raise ValueError('empty token tensor')
         pad = ids == self.cfg['padding_idx']
-        if bool((pad[:, :-1] & ~pad[:, 1:]).any()) or bool(pad[:, 0].any()):
-            raise ValueError('padding ids must be trailing and every utterance non-empty')
         f32 = dict(dtype=torch.float32, device=device)
+        # speaker (model.py:358-362): an int for the whole batch or a tensor of B ids; single-speaker checkpoints
+        # ignore it like the reference (speaker_emb is None)
+        spk, spk_ids = -1, None
+        if self.cfg['n_speakers'] > 1:
+            if torch.is_tensor(speaker) and speaker.numel() > 1:
+                spk_ids = speaker.to(device=device, dtype=torch.int64).reshape(-1).contiguous()
+                if spk_ids.numel() != B:
+                    raise ValueError('speaker tensor must hold one id per utterance')
+            else:
+                spk = int(speaker)
+                if not 0 <= spk < self.cfg['n_speakers']:
+                    raise IndexError('speaker id %d out of range [0, %d)' % (spk, self.cfg['n_speakers']))
         with torch.cuda.device(device):
             handle = self._get_handle(device)
             stream = _lib.current_stream(device)
@@ -209,9 +221,12 @@ class FastPitch(nn.Module):
             ws = self._ws.get(nb, device)
             log_dur = torch.empty(B, L, **f32)
             pitch = torch.empty(B, L, **f32)
-            spk = int(speaker) if self.cfg['n_speakers'] > 1 else -1
-            _lib.check(lib.ttsb_fastpitch_encode(handle, _lib.ptr(ids), B, L, spk, _lib.ptr(log_dur), _lib.ptr(pitch),
-                                                 _lib.ptr(state), _lib.ptr(ws), ws.numel(), stream))
+            _lib.check(lib.ttsb_fastpitch_encode(handle, _lib.ptr(ids), B, L, spk, _lib.ptr(spk_ids), _lib.ptr(log_dur),
+                                                 _lib.ptr(pitch), _lib.ptr(state), _lib.ptr(ws), ws.numel(), stream))
+            if taps is not None:            # parity tests: the encoder output before conditioning (model.py:364)
+                enc = torch.empty(B, L, self.cfg['symbols_embedding_dim'], dtype=torch.float16, device=device)
+                _lib.check(lib.ttsb_fastpitch_read_enc_out(handle, B, L, _lib.ptr(state), _lib.ptr(enc), stream))
+                taps['enc_out'] = enc.float()
             pitch_pred = pitch[:, None, :]
             if pitch_transform is not None:                         # model.py:373-380
                 if float(self.pitch_std[0]) == 0.0:
@@ -225,11 +240,20 @@ class FastPitch(nn.Module):
             dur_pred = torch.empty(B, L, **f32)
             energy_pred = torch.empty(B, L, **f32) if (self.energy_conditioning and e_tgt is None) else None
             dec_lens = torch.empty(B, dtype=torch.int64, device=device)
+            summary = torch.empty(2, dtype=torch.int32, device=device)
             _lib.check(lib.ttsb_fastpitch_condition(handle, B, L, _lib.ptr(log_dur), _lib.ptr(pitch_in), _lib.ptr(e_tgt),
                                                     _lib.ptr(d_tgt), float(pace), float(max_duration),
                                                     _lib.ptr(dur_pred), _lib.ptr(energy_pred), _lib.ptr(dec_lens),
-                                                    _lib.ptr(state), _lib.ptr(ws), ws.numel(), stream))
-            T = int(dec_lens.max())          # the reference's own host sync (model.py:76)
+                                                    _lib.ptr(summary), _lib.ptr(state), _lib.ptr(ws), ws.numel(), stream))
+            # THE host sync of the call — the reference's own (model.py:76: max(dec_lens) sizes the decoder batch). The
+            # input checks ride on it: ids were validated on the device by encode (no extra reductions or syncs)
+            T, status = summary.tolist()
+            if status & 1:
+                raise IndexError('token id out of range [0, %d)' % self.cfg['n_symbols'])
+            if status & 4:
+                raise IndexError('speaker id out of range [0, %d)' % self.cfg['n_speakers'])
+            if status & 2:
+                raise ValueError('padding ids must be trailing and every utterance non-empty')
             if T <= 0:
                 raise RuntimeError('all predicted durations are zero')
             nb = lib.ttsb_fastpitch_workspace_bytes(handle, B, L, T)
