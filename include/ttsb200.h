@@ -58,6 +58,13 @@ int64_t ttsb_launch_count(void);
 /* Debug: device buffer of 256 x 64 int64 that conv_tc_kernel fills with clock64() stamps per CTA
  * (NULL disables). Slot meaning in csrc/conv_tc.cu (tl_mark). Not for production use. */
 int ttsb_debug_set_timeline(void* d_buf);
+/* Stage profiler (bench.py's per-kernel rooflines): while enabled, the model entry points record a CUDA event on the
+ * caller's stream before each stage; ttsb_prof_collect synchronises the device and returns the summed device time per
+ * stage tag in milliseconds (tags: csrc/common.cuh ProfTag, mirrored in bench.py; index 0 = untagged gaps). Not thread-safe;
+ * meant for a dedicated measurement pass, never for the timed region of a throughput number. */
+int ttsb_prof_enable(int on);
+int ttsb_prof_n_tags(void);
+int ttsb_prof_collect(double* h_ms_by_tag, int n_tags);
 /* Device-side error flag raised by bounded mbarrier waits (0 = none). Synchronises the device. */
 int ttsb_device_error_flag(int* h_flag);
 
@@ -169,12 +176,27 @@ size_t ttsb_tacotron2_workspace_bytes(const ttsb_tacotron2_t* h, int B, int L, i
 int ttsb_tacotron2_encode(ttsb_tacotron2_t* h, const int64_t* d_tokens, const int32_t* d_lengths,
                           const int64_t* d_speaker_ids, int B, int L, int max_steps, void* d_state,
                           void* d_workspace, size_t workspace_bytes, void* stream);
+/* Runs decoder steps [step0, step0 + n_steps) as ONE cooperative launch (persistent kernel, grid barriers between the
+ * phases of a step). early_stop != 0: the chunk ends after the first step at which every utterance has raised its stop
+ * gate (torchaudio:850, decided on the device). h_done_step (host int[2], optional): after the call — which then
+ * synchronises the stream — [0] = that step or -1, [1] = input status bits raised by encode (1: a token id outside
+ * [0, n_symbol), 4: a speaker id outside [0, num_speakers); the gathers themselves were clamped). */
 int ttsb_tacotron2_decode(ttsb_tacotron2_t* h, int B, int L, int max_steps, int step0, int n_steps,
-                          const uint8_t* d_masks, float gate_threshold, void* d_state, int* h_done_step,
-                          void* stream);
+                          const uint8_t* d_masks, float gate_threshold, int early_stop, void* d_state,
+                          int* h_done_step, void* stream);
 int ttsb_tacotron2_finish(ttsb_tacotron2_t* h, int B, int L, int max_steps, int T, float* d_mel,
                           int32_t* d_mel_lengths, float* d_alignments, void* d_mel_cl, void* d_state,
                           void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Wrapper post-processing of a whole batch in one launch (replaces the per-utterance Python loop of
+ * models/tacotron2/networks.py:192-206 with its host sync per utterance): for utterance b with d_cols[b] >= 0 the mel is
+ * cut where alignments[b, :, d_cols[b]] first reaches 80 % of its maximum and its last kept frame is repeated three times
+ * (truncate_mel, :44-49); then, if rate != 1, it is resized in time to int(len / rate) frames with torch's bicubic kernel
+ * (resize_mel, :52-67). d_mel [B,n_mel,T] fp32, d_align [B,T,L] fp32 (may be NULL when d_cols is NULL), d_out
+ * [B,n_mel,T_out] fp32 (frames beyond d_out_lens[b] are zero), d_out_lens [B] int32 (clipped to T_out). */
+int ttsb_tacotron2_postprocess(const float* d_mel, const int32_t* d_mel_lens, const float* d_align, const int32_t* d_cols,
+                               double rate, int B, int n_mel, int T, int L, int T_out, float* d_out, int32_t* d_out_lens,
+                               void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Single conv site, for parity tests of the dense-contraction kernel in isolation.

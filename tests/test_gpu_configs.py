@@ -231,3 +231,19 @@ print("ok", [int(w.numel()) for w in wavs])
     r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stdout.strip().startswith('ok')
+
+
+def test_generator_cuda_graph_replay_matches_stream_launches(vocoder):
+    """Small batches are launch-bound; a captured graph of the generator's launch train must reproduce the stream
+    launches bit for bit, also on new inputs of the same shape."""
+    gen = torch.Generator().manual_seed(9)
+    mel = torch.clamp(torch.randn(1, 80, 64, generator=gen) * 2 - 5, -11.5129, 2.0).to(_dev())
+    ref = vocoder(mel).clone()
+    replay = vocoder.capture_graph(mel)
+    out = replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out.view(-1), ref.view(-1))
+    mel2 = torch.clamp(torch.randn(1, 80, 64, generator=gen) * 2 - 5, -11.5129, 2.0).to(_dev())
+    out2 = replay(mel2).clone()
+    assert torch.equal(out2.view(-1), vocoder(mel2).view(-1))
+    assert vocoder.capture_graph(mel2) is not None and len(vocoder._graphs) == 1     # same shape: same graph

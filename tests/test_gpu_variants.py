@@ -21,7 +21,7 @@ def _run(tmp_path, name, env_extra):
         pytest.fail('GPU tests need a CUDA device')
     out = os.path.join(str(tmp_path), name + '.npz')
     env = dict(os.environ)
-    for k in ('TTSB_PAIR', 'TTSB_TMA_OUT', 'TTSB_ATTENTION', 'TTSB_CLUSTER', 'TTSB_PAIR_XFORM_FINAL'):
+    for k in ('TTSB_PAIR', 'TTSB_TMA_OUT', 'TTSB_ATTENTION', 'TTSB_CLUSTER', 'TTSB_PAIR_SMEM_RES', 'TTSB_ACT_CHAIN'):
         env.pop(k, None)
     env.update(env_extra)
     r = subprocess.run([sys.executable, HELPER, out], env=env, capture_output=True, text=True, timeout=600)
@@ -54,13 +54,18 @@ def test_tma_store_epilogue_is_bit_exact(default_run, tmp_path):
 
 
 def test_attention_kernels_agree(default_run, tmp_path):
-    other = _run(tmp_path, 'simt', {'TTSB_ATTENTION': 'simt'})
-    assert other['dec_lens'].tolist() == default_run['dec_lens'].tolist()
-    assert np.abs(default_run['mel'] - other['mel']).max() < tol.MEL_LINF
+    """default = tcgen05 (attention_tc.cu: both contractions on the 5th-generation tensor cores) against the two older
+    generations kept as cross-checks: mma.sync m16n8k16 and plain fp32 FMA."""
+    for name in ('mma', 'simt'):
+        other = _run(tmp_path, name, {'TTSB_ATTENTION': name})
+        assert other['dec_lens'].tolist() == default_run['dec_lens'].tolist()
+        assert np.abs(default_run['mel'] - other['mel']).max() < tol.MEL_LINF
 
 
 def test_weight_multicast_and_transform_placement_do_not_change_results(default_run, tmp_path):
     a = _run(tmp_path, 'nocluster', {'TTSB_CLUSTER': '1'})
     assert np.array_equal(default_run['wav'], a['wav'])
-    b = _run(tmp_path, 'xformfinal', {'TTSB_PAIR_XFORM_FINAL': '1'})
+    b = _run(tmp_path, 'globalres', {'TTSB_PAIR_SMEM_RES': '0'})      # residual from global memory instead of the x panel
     assert np.array_equal(default_run['wav'], b['wav'])
+    c = _run(tmp_path, 'rawchain', {'TTSB_ACT_CHAIN': '0'})           # round-1 data flow: raw + activated copies
+    assert _rel_rms(default_run['wav'], c['wav']) < tol.WAV_REL_RMS

@@ -47,6 +47,9 @@ _SIGNATURES = {
     'ttsb_launch_count': (c_int64, []),
     'ttsb_device_error_flag': (c_int, [ctypes.POINTER(c_int)]),
     'ttsb_debug_set_timeline': (c_int, [c_void_p]),
+    'ttsb_prof_enable': (c_int, [c_int]),
+    'ttsb_prof_n_tags': (c_int, []),
+    'ttsb_prof_collect': (c_int, [ctypes.POINTER(ctypes.c_double), c_int]),
     'ttsb_hifigan_create': (c_int, [ctypes.POINTER(HifiganConfig), ctypes.POINTER(TensorDesc), c_int, c_int,
                                     ctypes.POINTER(c_void_p)]),
     'ttsb_hifigan_destroy': (None, [c_void_p]),
@@ -73,10 +76,12 @@ _SIGNATURES = {
     'ttsb_tacotron2_workspace_bytes': (c_size_t, [c_void_p, c_int, c_int, c_int]),
     'ttsb_tacotron2_encode': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                       c_size_t, c_void_p]),
-    'ttsb_tacotron2_decode': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_float, c_void_p,
+    'ttsb_tacotron2_decode': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_float, c_int, c_void_p,
                                       ctypes.POINTER(c_int), c_void_p]),
     'ttsb_tacotron2_finish': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_size_t, c_void_p]),
+    'ttsb_tacotron2_postprocess': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_double, c_int, c_int, c_int, c_int, c_int,
+                                           c_void_p, c_void_p, c_void_p]),
     'ttsb_conv1d_create': (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                    ctypes.POINTER(c_void_p)]),
     'ttsb_conv1d_destroy': (None, [c_void_p]),

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libttsb200.so")
 OBJ_DIR = os.path.join(HERE, "build")
-SOURCES = ["conv_host.cu", "conv_tc.cu", "conv_tc2.cu", "conv_pair.cu", "kernels_misc.cu", "denoiser.cu", "hifigan.cu", "fastpitch.cu", "tacotron2.cu", "capi.cu"]
+SOURCES = ["conv_host.cu", "conv_tc.cu", "conv_tc2.cu", "conv_pair.cu", "kernels_misc.cu", "attention_tc.cu", "denoiser.cu", "hifigan.cu", "fastpitch.cu", "tacotron2.cu", "capi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math" if False else "-DTTSB_NO_FAST_MATH"]
 

@@ -66,6 +66,15 @@ int ttsb_device_error_flag(int* h_flag) {
     });
 }
 
+int ttsb_prof_enable(int on) { return prof_enable(on); }
+int ttsb_prof_n_tags(void) { return PROF_N_TAGS; }
+int ttsb_prof_collect(double* h_ms_by_tag, int n_tags) {
+    return guarded_call([&]() -> int {
+    TTSB_REQUIRE(h_ms_by_tag != nullptr && n_tags > 0, "null argument");
+    return prof_collect(h_ms_by_tag, n_tags);
+    });
+}
+
 int ttsb_debug_set_timeline(void* d_buf) {
     return guarded_call([&]() -> int {
     global_runtime().timeline = static_cast<long long*>(d_buf);

@@ -96,6 +96,19 @@ struct DeviceGuard {
     ::ttsb::DeviceGuard _ttsb_guard(device);         \
     TTSB_CHECK_CUDA(_ttsb_guard.status)
 
+// Stage profiler for bench.py's per-kernel rooflines (ttsb_prof_* in the C ABI): when enabled, every stage of the model
+// entry points records a CUDA event ON THE LAUNCHING STREAM before its first launch; the device time between two
+// consecutive marks is charged to the earlier mark's tag. Off (the default) it is one predictable branch per stage.
+enum ProfTag : int {
+    PROF_NONE = 0,        // gap between entry points / untagged work
+    PROF_VOC_PRE, PROF_VOC_UPS0, PROF_VOC_S0, PROF_VOC_UPS1, PROF_VOC_S1, PROF_VOC_UPS2, PROF_VOC_S2, PROF_VOC_UPS3,
+    PROF_VOC_S3, PROF_VOC_POST, PROF_VOC_PACK,
+    PROF_FP_EMBED, PROF_FP_QKV_O, PROF_FP_ATTENTION, PROF_FP_FFN, PROF_FP_PREDICTORS, PROF_FP_GLUE, PROF_FP_REGULATE,
+    PROF_FP_PROJ,
+    PROF_N_TAGS
+};
+void prof_mark(int tag, cudaStream_t stream);
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 

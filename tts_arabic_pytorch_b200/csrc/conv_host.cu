@@ -15,6 +15,46 @@ static long long g_launches = 0;
 void count_launch(int n) { __atomic_fetch_add(&g_launches, static_cast<long long>(n), __ATOMIC_RELAXED); }
 long long launch_count() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
+// ---- stage profiler (see common.cuh) ----
+namespace {
+struct Prof {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> tag;
+    size_t used = 0;
+};
+Prof g_prof;
+}  // namespace
+void prof_mark(int tag, cudaStream_t stream) {
+    if (!g_prof.on) return;
+    if (g_prof.used == g_prof.ev.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        g_prof.ev.push_back(e);
+        g_prof.tag.push_back(0);
+    }
+    g_prof.tag[g_prof.used] = tag;
+    cudaEventRecord(g_prof.ev[g_prof.used], stream);
+    ++g_prof.used;
+}
+int prof_enable(int on) {
+    g_prof.on = on != 0;
+    g_prof.used = 0;
+    return 0;
+}
+int prof_collect(double* ms_by_tag, int n_tags) {
+    for (int i = 0; i < n_tags; ++i) ms_by_tag[i] = 0.0;
+    TTSB_CHECK_CUDA(cudaDeviceSynchronize());
+    for (size_t i = 0; i + 1 < g_prof.used; ++i) {
+        float ms = 0.f;
+        TTSB_CHECK_CUDA(cudaEventElapsedTime(&ms, g_prof.ev[i], g_prof.ev[i + 1]));
+        const int t = g_prof.tag[i];
+        if (t >= 0 && t < n_tags) ms_by_tag[t] += ms;
+    }
+    g_prof.used = 0;
+    return 0;
+}
+
 int conv_forward_tc(const ConvLayer& L, const ConvRuntime& rt, const __half* in, int ld_in, int B,
                     int T, const EpiParams& epi, cudaStream_t stream);
 int conv_forward_tc2(const ConvLayer& L, const ConvRuntime& rt, const __half* in, int ld_in, int B,

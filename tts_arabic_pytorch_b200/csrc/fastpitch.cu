@@ -139,7 +139,7 @@ struct State {  // persistent between encode / condition / decode
     __half* x;  // [B,L,D]
 };
 struct Scratch {
-    __half *qkv, *att, *x, *hid, *p1;
+    __half *qkv, *att, *x, *hid, *p1, *vt;
 };
 
 State carve_state(const ttsb_fastpitch* h, void* p, int B, int L, size_t* bytes) {
@@ -162,6 +162,7 @@ Scratch carve_scratch(const ttsb_fastpitch* h, void* p, int B, int R, size_t* by
     s.x = c.take<__half>(rows * h->cfg.d_model);
     s.hid = c.take<__half>(rows * h->cfg.d_inner);
     s.p1 = c.take<__half>(rows * h->cfg.pred_filter);
+    s.vt = c.take<__half>(attention_tc_scratch_bytes(B, R) / sizeof(__half));
     if (bytes) *bytes = c.off + 256;
     return s;
 }
@@ -173,16 +174,20 @@ int run_fft_layer(const ttsb_fastpitch* h, const FftLayer& l, const ConvRuntime&
     {
         EpiParams e;
         e.out_raw = sc.qkv; e.ld_raw = 3 * dh;
+        prof_mark(PROF_FP_QKV_O, stream);
         TTSB_PROPAGATE(conv_forward(l.qkv, rt, x, D, B, R, e, stream));
     }
-    TTSB_PROPAGATE(launch_attention(sc.qkv, lens, B, R, 1.f / sqrtf(static_cast<float>(dh)), sc.att, stream));
+    prof_mark(PROF_FP_ATTENTION, stream);
+    TTSB_PROPAGATE(launch_attention(sc.qkv, lens, B, R, 1.f / sqrtf(static_cast<float>(dh)), sc.att, stream, sc.vt, rt.err_flag));
     {
         EpiParams e;
         e.residual = x; e.ld_res = D;
         e.ln_g = l.ln1_g; e.ln_b = l.ln1_b;
         e.lens = lens;
         e.out_raw = x; e.ld_raw = D;
+        prof_mark(PROF_FP_QKV_O, stream);
         TTSB_PROPAGATE(conv_forward(l.o, rt, sc.att, dh, B, R, e, stream));
+        prof_mark(PROF_FP_FFN, stream);
     }
     {
         EpiParams e;
@@ -204,6 +209,7 @@ int run_fft_layer(const ttsb_fastpitch* h, const FftLayer& l, const ConvRuntime&
 int run_predictor(const ttsb_fastpitch* h, const Predictor& p, const ConvRuntime& rt, const __half* x,
                   const int* lens, int B, int L, const Scratch& sc, float* out, cudaStream_t stream) {
     const int D = h->cfg.d_model, F = h->cfg.pred_filter;
+    prof_mark(PROF_FP_PREDICTORS, stream);
     {
         EpiParams e;
         e.pre_ln_relu = 1; e.ln_g = p.n0_g; e.ln_b = p.n0_b;
@@ -323,6 +329,7 @@ int ttsb_fastpitch_encode(ttsb_fastpitch_t* h, const int64_t* d_ids, int B, int 
     Scratch sc = carve_scratch(h, d_workspace, B, L, nullptr);
     const int D = h->cfg.d_model;
     const bool use_spk = h->spk_table != nullptr && (speaker >= 0 || d_speaker_ids != nullptr);
+    prof_mark(PROF_FP_EMBED, stream);
     TTSB_CHECK_CUDA(cudaMemsetAsync(st.summary, 0, 4 * sizeof(int), stream));
     TTSB_PROPAGATE(launch_ids_to_lens(d_ids, B, L, h->cfg.n_symbols, use_spk ? d_speaker_ids : nullptr, h->cfg.n_speakers,
                                       st.lens, st.summary + 1, stream));
@@ -331,6 +338,7 @@ int ttsb_fastpitch_encode(ttsb_fastpitch_t* h, const int64_t* d_ids, int B, int 
     for (const FftLayer& l : h->enc) TTSB_PROPAGATE(run_fft_layer(h, l, rt, st.x, st.lens, B, L, sc, stream));
     TTSB_PROPAGATE(run_predictor(h, h->dur, rt, st.x, st.lens, B, L, sc, d_log_dur, stream));
     TTSB_PROPAGATE(run_predictor(h, h->pitch, rt, st.x, st.lens, B, L, sc, d_pitch, stream));
+    prof_mark(PROF_NONE, stream);
     return 0;
     });
 }
@@ -364,6 +372,7 @@ int ttsb_fastpitch_condition(ttsb_fastpitch_t* h, int B, int L, const float* d_l
     const int D = h->cfg.d_model;
     // enc_out = enc_out + pitch_emb(pitch)   (model.py:382-386); masked copy is what every later
     // consumer sees (energy predictor masks its input, padded tokens get zero frames)
+    prof_mark(PROF_FP_GLUE, stream);
     TTSB_PROPAGATE(launch_scalar_embed_add(st.x, d_pitch_in, h->pitch_emb.w, h->pitch_emb.b, st.lens, B, L, D, 1, stream));
     if (h->cfg.energy_conditioning) {
         const float* energy = d_energy_tgt;
@@ -372,6 +381,7 @@ int ttsb_fastpitch_condition(ttsb_fastpitch_t* h, int B, int L, const float* d_l
             TTSB_PROPAGATE(run_predictor(h, h->energy, rt, st.x, st.lens, B, L, sc, d_energy_pred, stream));
             energy = d_energy_pred;
         }
+        prof_mark(PROF_FP_GLUE, stream);
         TTSB_PROPAGATE(launch_scalar_embed_add(st.x, energy, h->energy_emb.w, h->energy_emb.b, st.lens, B, L, D, 1, stream));
     }
     TTSB_CHECK_CUDA(cudaMemsetAsync(st.summary, 0, sizeof(int), stream));     // [0] only: the input status of encode stays
@@ -379,6 +389,7 @@ int ttsb_fastpitch_condition(ttsb_fastpitch_t* h, int B, int L, const float* d_l
                                     st.dec_lens, d_dec_lens, st.summary, stream));
     if (d_summary)
         TTSB_CHECK_CUDA(cudaMemcpyAsync(d_summary, st.summary, 2 * sizeof(int), cudaMemcpyDeviceToDevice, stream));
+    prof_mark(PROF_NONE, stream);
     return 0;
     });
 }
@@ -396,6 +407,7 @@ int ttsb_fastpitch_decode(ttsb_fastpitch_t* h, int B, int L, int T, float* d_mel
     State st = carve_state(h, d_state, B, L, nullptr);
     Scratch sc = carve_scratch(h, d_workspace, B, std::max(L, T), nullptr);
     const int D = h->cfg.d_model;
+    prof_mark(PROF_FP_REGULATE, stream);
     TTSB_PROPAGATE(launch_regulate(st.x, st.cum, st.dec_lens, h->inv_freq_dec, B, L, T, D, sc.x, stream));
     for (const FftLayer& l : h->dec) TTSB_PROPAGATE(run_fft_layer(h, l, rt, sc.x, st.dec_lens, B, T, sc, stream));
     EpiParams e;
@@ -404,7 +416,9 @@ int ttsb_fastpitch_decode(ttsb_fastpitch_t* h, int B, int L, int T, float* d_mel
         e.lens = st.dec_lens;
         e.out_raw = static_cast<__half*>(d_mel_cl); e.ld_raw = h->mel_ld;
     }
+    prof_mark(PROF_FP_PROJ, stream);
     TTSB_PROPAGATE(conv_forward(h->proj, rt, sc.x, D, B, T, e, stream));
+    prof_mark(PROF_NONE, stream);
     return 0;
     });
 }

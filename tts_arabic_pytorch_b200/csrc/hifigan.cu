@@ -263,6 +263,7 @@ int ttsb_hifigan_forward(ttsb_hifigan_t* h, const float* d_mel_f32, const void* 
         const int* lens = d_lens ? d_lens + b0 : nullptr;
         const __half* mel_in;
         if (d_mel_f32) {
+            prof_mark(PROF_VOC_PACK, stream);
             TTSB_PROPAGATE(launch_pack_mel(d_mel_f32 + static_cast<size_t>(b0) * cfg.num_mels * T, lens, bc,
                                            cfg.num_mels, T, melp, h->mel_ld, stream));
             mel_in = melp;
@@ -274,6 +275,7 @@ int ttsb_hifigan_forward(ttsb_hifigan_t* h, const float* d_mel_f32, const void* 
             EpiParams e;
             e.lens = lens; e.len_mul = 1;
             e.out_act = NXT[cur]; e.ld_act = cfg.upsample_initial_channel; e.act_slope = 0.1f;
+            prof_mark(PROF_VOC_PRE, stream);
             TTSB_PROPAGATE(conv_forward(h->conv_pre, rt, mel_in, h->mel_ld, bc, T, e, stream));
         }
         int cin = cfg.upsample_initial_channel;
@@ -292,7 +294,9 @@ int ttsb_hifigan_forward(ttsb_hifigan_t* h, const float* d_mel_f32, const void* 
                     if (any_unfused) { e.out_act = LX0; e.ld_act = s * C; }
                 }
                 e.act_slope = kSlope;
+                prof_mark(i < 4 ? PROF_VOC_UPS0 + 2 * i : PROF_NONE, stream);
                 TTSB_PROPAGATE(conv_forward(h->ups[i], rt, NXT[cur], cin, bc, T * up, e, stream));
+                prof_mark(i < 4 ? PROF_VOC_S0 + 2 * i : PROF_NONE, stream);
             }
             up *= s;
             const int rows = T * up;
@@ -351,8 +355,10 @@ int ttsb_hifigan_forward(ttsb_hifigan_t* h, const float* d_mel_f32, const void* 
             cur ^= 1;
             cin = C;
         }
+        prof_mark(PROF_VOC_POST, stream);
         TTSB_PROPAGATE(launch_conv_post_tanh(NXT[cur], h->post_w, h->post_b, lens, h->hop, bc, T * h->hop,
                                              d_wav + static_cast<size_t>(b0) * T * h->hop, stream));
+        prof_mark(PROF_NONE, stream);
     }
     return 0;
     });

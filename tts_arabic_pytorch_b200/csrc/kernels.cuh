@@ -30,7 +30,11 @@ int launch_ids_to_lens(const int64_t* ids, int B, int L, int n_symbols, const in
 // single-head attention with key-padding mask (transformer.py:131-146), d_head = 64.
 // qkv: [B,S,192] fp16 (q|k|v), out: [B,S,64] fp16.
 int launch_attention(const __half* qkv, const int* lens, int B, int S, float scale, __half* out,
-                     cudaStream_t s);
+                     cudaStream_t s, __half* vt_scratch = nullptr, int* err_flag = nullptr);
+// the tcgen05 implementation (attention_tc.cu; the default): needs attention_tc_scratch_bytes(B, S) of scratch for V^T
+size_t attention_tc_scratch_bytes(int B, int S);
+int launch_attention_tc(const __half* qkv, const int* lens, int B, int S, float scale, __half* out, __half* vt_scratch,
+                        int* err_flag, cudaStream_t s);
 
 // x[b,l,:] = (x[b,l,:] + bias + sum_k w[:,k] * p[b,l+k-1]) * mask   (model.py:382-386,393-397:
 // Conv1d(1->D,k3,p1) of the per-token pitch / energy track added onto enc_out)

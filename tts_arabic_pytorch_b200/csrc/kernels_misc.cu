@@ -425,8 +425,12 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const __half* __rest
 
 static const int kAttSmem = 4 * 64 * 65 * sizeof(float);
 int launch_attention(const __half* qkv, const int* lens, int B, int S, float scale, __half* out,
-                     cudaStream_t s) {
-    static const bool use_simt = getenv("TTSB_ATTENTION") != nullptr && std::string(getenv("TTSB_ATTENTION")) == "simt";
+                     cudaStream_t s, __half* vt_scratch, int* err_flag) {
+    // TTSB_ATTENTION = tc (default: tcgen05, attention_tc.cu) | mma (mma.sync m16n8k16) | simt (fp32 FMA): the two older
+    // generations stay as on-GPU cross-checks
+    static const std::string mode = getenv("TTSB_ATTENTION") != nullptr ? std::string(getenv("TTSB_ATTENTION")) : std::string("tc");
+    if (mode == "tc" && vt_scratch != nullptr) return launch_attention_tc(qkv, lens, B, S, scale, out, vt_scratch, err_flag, s);
+    const bool use_simt = mode == "simt";
     dim3 grid(ceil_div(S, 64), B);
     if (!use_simt) {
         attention_mma_kernel<<<grid, 128, 0, s>>>(qkv, lens, S, scale, out);

@@ -54,6 +54,8 @@ int make_conv1d_layer(ConvLayer& L, const float* w, const float* bias, int cout,
 int make_convT1d_layer(ConvLayer& L, const float* w, const float* bias, int cin, int cout, int k,
                        int stride);
 int upload_f32(const float* h, size_t n, float** d);
+int prof_enable(int on);
+int prof_collect(double* ms_by_tag, int n_tags);
 
 struct Carver {
     uint8_t* base;

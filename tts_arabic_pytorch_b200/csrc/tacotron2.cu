@@ -14,6 +14,7 @@
 //   postnet   5 x [Conv1d k5 + BatchNorm(folded) (+tanh)] (tcgen05 conv kernel) + residual
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include "model_common.cuh"
 
 using namespace ttsb;
@@ -31,14 +32,19 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// dot(w_row[0:n] (fp16), x[0:n] (fp32)) by one warp; n % 8 == 0
+// State vectors that OTHER CTAs wrote earlier in the same launch (the persistent decoder below) must not come from this
+// SM's L1, which is not coherent: they are read with ld.global.cg (L2 only). Weights stay on the cached read-only path.
+__device__ __forceinline__ float4 ld_state4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+
+// dot(w_row[0:n] (fp16), x[0:n] (fp32)) by one warp; n % 8 == 0. kState: x is such a state vector in global memory.
+template <bool kState = false>
 __device__ __forceinline__ float warp_dot_h(const __half* __restrict__ w, const float* __restrict__ x, int n, int lane) {
     float acc = 0.f;
     for (int i = lane * 8; i < n; i += 256) {
         float f[8];
         load8h(w + i, f);
-        const float4 a = *reinterpret_cast<const float4*>(x + i);
-        const float4 b = *reinterpret_cast<const float4*>(x + i + 4);
+        const float4 a = kState ? ld_state4(x + i) : *reinterpret_cast<const float4*>(x + i);
+        const float4 b = kState ? ld_state4(x + i + 4) : *reinterpret_cast<const float4*>(x + i + 4);
         acc += f[0] * a.x + f[1] * a.y + f[2] * a.z + f[3] * a.w + f[4] * b.x + f[5] * b.y + f[6] * b.z + f[7] * b.w;
     }
     return warp_sum(acc);
@@ -47,10 +53,16 @@ __device__ __forceinline__ float warp_dot_h(const __half* __restrict__ w, const 
 // ------------------------------------------------------------------------------------------------
 // encoder pieces
 // ------------------------------------------------------------------------------------------------
-__global__ void t2_embed_kernel(const int64_t* __restrict__ ids, const float* __restrict__ emb, int D,
-                                __half* __restrict__ out) {
+// token / speaker ids are clamped into their tables; out-of-range values raise bits in *status (1 token, 4 speaker), which
+// the caller reads with the decoder's first host sync (nn.Embedding raises IndexError in the reference)
+__global__ void t2_embed_kernel(const int64_t* __restrict__ ids, const float* __restrict__ emb, int D, int n_symbol,
+                                int* __restrict__ status, __half* __restrict__ out) {
     const int row = blockIdx.x;
-    const int64_t id = ids[row];
+    int64_t id = ids[row];
+    if (id < 0 || id >= n_symbol) {
+        if (threadIdx.x == 0) atomicOr(status, 1);
+        id = id < 0 ? 0 : n_symbol - 1;
+    }
     for (int j = threadIdx.x; j < D; j += blockDim.x) out[static_cast<size_t>(row) * D + j] = __float2half(emb[id * D + j]);
 }
 
@@ -98,13 +110,19 @@ __global__ void __launch_bounds__(1024) t2_bilstm_kernel(const float* __restrict
 // memory = [enc_out (fp32, E) | speaker embedding (S)] and processed_memory = memory @ Wm^T
 __global__ void t2_memory_kernel(const float* __restrict__ enc, const float* __restrict__ spk_emb,
                                  const int64_t* __restrict__ spk_ids, const __half* __restrict__ wm, int L, int E,
-                                 int S, int A, float* __restrict__ memory, float* __restrict__ pmem) {
+                                 int S, int A, int num_speakers, int* __restrict__ status, float* __restrict__ memory,
+                                 float* __restrict__ pmem) {
     extern __shared__ float row[];  // [E+S]
     const int r = blockIdx.x;       // b*L + l
     const int b = r / L;
     const int M = E + S;
+    int64_t sp = S > 0 ? spk_ids[b] : 0;
+    if (S > 0 && (sp < 0 || sp >= num_speakers)) {
+        if (threadIdx.x == 0) atomicOr(status, 4);
+        sp = sp < 0 ? 0 : num_speakers - 1;
+    }
     for (int j = threadIdx.x; j < M; j += blockDim.x) {
-        const float v = j < E ? enc[static_cast<size_t>(r) * E + j] : spk_emb[spk_ids[b] * S + (j - E)];
+        const float v = j < E ? enc[static_cast<size_t>(r) * E + j] : spk_emb[sp * S + (j - E)];
         row[j] = v;
         memory[static_cast<size_t>(r) * M + j] = v;
     }
@@ -120,13 +138,12 @@ __global__ void t2_memory_kernel(const float* __restrict__ enc, const float* __r
 // decoder step kernels
 // ------------------------------------------------------------------------------------------------
 // prenet: frame [B,80] -> relu(W0 .) * m0 -> relu(W1 .) * m1 -> x [B,P]; masks are 0/1 bytes, scale 2
-__global__ void t2_prenet_kernel(const float* __restrict__ frame, const __half* __restrict__ w0,
-                                 const __half* __restrict__ w1, const uint8_t* __restrict__ m0,
-                                 const uint8_t* __restrict__ m1, int n_mel, int P, float* __restrict__ x) {
-    extern __shared__ float sm[];
+__device__ __forceinline__ void t2_prenet_body(float* sm, int b, const float* __restrict__ frame,
+                                               const __half* __restrict__ w0, const __half* __restrict__ w1,
+                                               const uint8_t* __restrict__ m0, const uint8_t* __restrict__ m1, int n_mel,
+                                               int P, float* __restrict__ x) {
     float* f = sm;            // [n_mel]
     float* h = sm + n_mel;    // [P]
-    const int b = blockIdx.x;
     for (int j = threadIdx.x; j < n_mel; j += blockDim.x) f[j] = frame[b * n_mel + j];
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
@@ -140,19 +157,23 @@ __global__ void t2_prenet_kernel(const float* __restrict__ frame, const __half* 
         if (lane == 0) x[b * P + o] = fmaxf(d, 0.f) * (m1[b * P + o] ? 2.f : 0.f);
     }
 }
+__global__ void t2_prenet_kernel(const float* __restrict__ frame, const __half* __restrict__ w0,
+                                 const __half* __restrict__ w1, const uint8_t* __restrict__ m0,
+                                 const uint8_t* __restrict__ m1, int n_mel, int P, float* __restrict__ x) {
+    extern __shared__ float sm[];
+    t2_prenet_body(sm, blockIdx.x, frame, w0, w1, m0, m1, n_mel, P, x);
+}
 
 // LSTMCell: gates = W_ih [x1|x2] + W_hh h + bias; block = 8 warps = 2 hidden units x 4 gates, all B
 // utterances (B <= 64 via a loop over groups of 8). h_in / h_out ping-pong, c in place.
-__global__ void __launch_bounds__(256) t2_lstm_cell_kernel(const float* __restrict__ x1, int n1,
-                                                           const float* __restrict__ x2, int n2,
-                                                           const float* __restrict__ h_in, float* __restrict__ h_out,
-                                                           float* __restrict__ c, const __half* __restrict__ w_ih,
-                                                           const __half* __restrict__ w_hh, const float* __restrict__ bias,
-                                                           int H, int B) {
-    __shared__ float g_s[2][4][64];
+__device__ __forceinline__ void t2_lstm_cell_body(float (*g_s)[4][64], int vb, const float* __restrict__ x1, int n1,
+                                                  const float* __restrict__ x2, int n2, const float* __restrict__ h_in,
+                                                  float* __restrict__ h_out, float* __restrict__ c,
+                                                  const __half* __restrict__ w_ih, const __half* __restrict__ w_hh,
+                                                  const float* __restrict__ bias, int H, int B) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ju = warp >> 2, gate = warp & 3;
-    const int j = blockIdx.x * 2 + ju;
+    const int j = vb * 2 + ju;
     const int grow = gate * H + j;
     const int n_in = n1 + n2;
     const __half* wi = w_ih + static_cast<size_t>(grow) * n_in;
@@ -171,8 +192,8 @@ __global__ void __launch_bounds__(256) t2_lstm_cell_kernel(const float* __restri
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 if (b0 + q < B) {
-                    const float4 a = *reinterpret_cast<const float4*>(src + static_cast<size_t>(b0 + q) * stride + off);
-                    const float4 bb = *reinterpret_cast<const float4*>(src + static_cast<size_t>(b0 + q) * stride + off + 4);
+                    const float4 a = ld_state4(src + static_cast<size_t>(b0 + q) * stride + off);
+                    const float4 bb = ld_state4(src + static_cast<size_t>(b0 + q) * stride + off + 4);
                     acc[q] += f[0] * a.x + f[1] * a.y + f[2] * a.z + f[3] * a.w + f[4] * bb.x + f[5] * bb.y + f[6] * bb.z + f[7] * bb.w;
                 }
             }
@@ -187,7 +208,7 @@ __global__ void __launch_bounds__(256) t2_lstm_cell_kernel(const float* __restri
     if (threadIdx.x < 2 * B && threadIdx.x < 128) {
         const int u = threadIdx.x / B, b = threadIdx.x % B;
         if (u < 2) {
-            const int jj = blockIdx.x * 2 + u;
+            const int jj = vb * 2 + u;
             const float ig = sigmoidf_(g_s[u][0][b]), fg = sigmoidf_(g_s[u][1][b]);
             const float gg = tanhf(g_s[u][2][b]), og = sigmoidf_(g_s[u][3][b]);
             const float cn = fg * c[static_cast<size_t>(b) * H + jj] + ig * gg;
@@ -196,27 +217,34 @@ __global__ void __launch_bounds__(256) t2_lstm_cell_kernel(const float* __restri
         }
     }
 }
+__global__ void __launch_bounds__(256) t2_lstm_cell_kernel(const float* __restrict__ x1, int n1,
+                                                           const float* __restrict__ x2, int n2,
+                                                           const float* __restrict__ h_in, float* __restrict__ h_out,
+                                                           float* __restrict__ c, const __half* __restrict__ w_ih,
+                                                           const __half* __restrict__ w_hh, const float* __restrict__ bias,
+                                                           int H, int B) {
+    __shared__ float g_s[2][4][64];
+    t2_lstm_cell_body(g_s, blockIdx.x, x1, n1, x2, n2, h_in, h_out, c, w_ih, w_hh, bias, H, B);
+}
 
 // location-sensitive attention for one utterance per block (torchaudio:203-255)
-__global__ void __launch_bounds__(256) t2_attention_kernel(const float* __restrict__ ah, const float* __restrict__ memory,
-                                                           const float* __restrict__ pmem, const int* __restrict__ lens,
-                                                           const __half* __restrict__ wq, const float* __restrict__ wloc_conv,
-                                                           const float* __restrict__ wloc_dense, const float* __restrict__ v,
-                                                           float* __restrict__ aw, float* __restrict__ awc,
-                                                           float* __restrict__ ctx, float* __restrict__ align_out,
-                                                           int L, int H, int M, int A, int NF, int KL) {
-    extern __shared__ float sm[];
+__device__ __forceinline__ void t2_attention_body(float* sm, int b, const float* __restrict__ ah,
+                                                  const float* __restrict__ memory, const float* __restrict__ pmem,
+                                                  const int* __restrict__ lens, const __half* __restrict__ wq,
+                                                  const float* __restrict__ wloc_conv, const float* __restrict__ wloc_dense,
+                                                  const float* __restrict__ v, float* __restrict__ aw, float* __restrict__ awc,
+                                                  float* __restrict__ ctx, float* __restrict__ align_out, int L, int H, int M,
+                                                  int A, int NF, int KL) {
     float* q = sm;                 // [A]
     float* w_prev = q + A;         // [L + KL - 1] padded previous weights
     float* w_cum = w_prev + L + KL; // [L + KL - 1]
     float* e = w_cum + L + KL;     // [L]
     float* red = e + L;            // [32]
-    const int b = blockIdx.x;
     const int len = lens[b];
     const int pad = (KL - 1) / 2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     for (int a = warp; a < A; a += nwarp) {
-        const float d = warp_dot_h(wq + static_cast<size_t>(a) * H, ah + static_cast<size_t>(b) * H, H, lane);
+        const float d = warp_dot_h<true>(wq + static_cast<size_t>(a) * H, ah + static_cast<size_t>(b) * H, H, lane);
         if (lane == 0) q[a] = d;
     }
     for (int i = threadIdx.x; i < L + KL - 1; i += blockDim.x) {
@@ -237,7 +265,8 @@ __global__ void __launch_bounds__(256) t2_attention_kernel(const float* __restri
             }
             for (int a = lane; a < A; a += 32) {
                 float s = q[a] + pmem[(static_cast<size_t>(b) * L + l) * A + a];
-                for (int nf = 0; nf < NF; ++nf) s += wloc_dense[a * NF + nf] * __shfl_sync(0xffffffffu, f, nf);
+                // wloc_dense is stored TRANSPOSED ([NF][A]): the lanes of a warp (consecutive a) read one line per filter
+                for (int nf = 0; nf < NF; ++nf) s += wloc_dense[nf * A + a] * __shfl_sync(0xffffffffu, f, nf);
                 part += v[a] * tanhf(s);
             }
         }
@@ -280,6 +309,17 @@ __global__ void __launch_bounds__(256) t2_attention_kernel(const float* __restri
         ctx[static_cast<size_t>(b) * M + m] = acc;
     }
 }
+__global__ void __launch_bounds__(256) t2_attention_kernel(const float* __restrict__ ah, const float* __restrict__ memory,
+                                                           const float* __restrict__ pmem, const int* __restrict__ lens,
+                                                           const __half* __restrict__ wq, const float* __restrict__ wloc_conv,
+                                                           const float* __restrict__ wloc_dense, const float* __restrict__ v,
+                                                           float* __restrict__ aw, float* __restrict__ awc,
+                                                           float* __restrict__ ctx, float* __restrict__ align_out,
+                                                           int L, int H, int M, int A, int NF, int KL) {
+    extern __shared__ float sm[];
+    t2_attention_body(sm, blockIdx.x, ah, memory, pmem, lens, wq, wloc_conv, wloc_dense, v, aw, awc, ctx, align_out, L, H, M, A,
+                      NF, KL);
+}
 
 // mel frame + gate: rows 0..n_mel-1 of W are linear_projection, row n_mel is gate_layer; one warp per row
 __global__ void __launch_bounds__(256) t2_project_kernel(const float* __restrict__ dh, const float* __restrict__ ctx,
@@ -292,8 +332,8 @@ __global__ void __launch_bounds__(256) t2_project_kernel(const float* __restrict
     if (o > n_mel) return;
     const __half* wr = w + static_cast<size_t>(o) * (H + M);
     for (int b = 0; b < B; ++b) {
-        const float d = warp_dot_h(wr, dh + static_cast<size_t>(b) * H, H, lane) +
-                        warp_dot_h(wr + H, ctx + static_cast<size_t>(b) * M, M, lane) + bias[o];
+        const float d = warp_dot_h<true>(wr, dh + static_cast<size_t>(b) * H, H, lane) +
+                        warp_dot_h<true>(wr + H, ctx + static_cast<size_t>(b) * M, M, lane) + bias[o];
         if (lane == 0) {
             if (o < n_mel) {
                 frame[b * n_mel + o] = d;
@@ -320,6 +360,179 @@ __global__ void t2_bookkeep_kernel(const float* __restrict__ gate, int* __restri
     if (threadIdx.x == 0 && all && *done_step < 0) *done_step = step;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Persistent decoder: ONE cooperative launch runs a whole chunk of autoregressive steps (torchaudio _Decoder.infer
+// :779-866 / decode :611-684). The six per-step launches above cost ~330 us per step at batch 8 on a B200 — host launch
+// rate, not arithmetic (round-2 bench, config 4) — against a weight-bandwidth floor of ~5 us. Here the same phase bodies
+// run inside a step loop, separated by grid-wide barriers:
+//     A  attention LSTM cell      all CTAs (2 hidden units x 4 gates per virtual block, all utterances)
+//     B  attention                one CTA per utterance
+//     C  decoder LSTM cell        all CTAs
+//     D  projection + stop bookkeeping + the NEXT step's prenet      one CTA per utterance
+// i.e. four barriers per step. State other CTAs wrote is read with ld.global.cg (see ld_state4). The stop decision
+// (torch.all(finished), torchaudio:850) is taken on the device after phase D; the host looks at it once per chunk.
+// ------------------------------------------------------------------------------------------------
+struct T2PersistArgs {
+    int B, L, H, M, P, A, NF, KL, n_mel, max_steps, step0, n_steps, early_stop;
+    float gate_threshold;
+    const uint8_t* masks;            // [n_steps, 2, B, P]
+    const int* lens;
+    const float *memory, *pmem;
+    float *ah[2], *ac, *dh[2], *dc, *aw, *awc, *ctx, *frame, *x, *gate, *frames, *align;
+    int *finished, *mel_lens, *done_step;
+    unsigned* bar;                   // grid barrier counter (zeroed before the launch)
+    int* err_flag;
+    const __half *pre_w0, *pre_w1, *arnn_wih, *arnn_whh, *drnn_wih, *drnn_whh, *w_query, *w_proj;
+    const float *arnn_b, *drnn_b, *loc_conv, *loc_dense, *att_v, *b_proj;
+};
+
+// LSTMCell for the persistent decoder: a 1024-thread CTA owns 8 hidden units (warp = 4 * unit + gate) and first stages
+// the input vectors [x1 | x2 | h] of up to 8 utterances in shared memory — every gate row of the CTA multiplies the same
+// vectors, and reading them per warp through ld.global.cg (no L1 in a persistent kernel, see ld_state4) cost ~250 MB of
+// L2 traffic per cell and step. Same per-lane accumulation order as t2_lstm_cell_body: identical results.
+__device__ __forceinline__ void t2_lstm_cell_staged(float* st, float (*g_s)[4][64], int cta, const float* __restrict__ x1,
+                                                    int n1, const float* __restrict__ x2, int n2,
+                                                    const float* __restrict__ h_in, float* __restrict__ h_out,
+                                                    float* __restrict__ c, const __half* __restrict__ w_ih,
+                                                    const __half* __restrict__ w_hh, const float* __restrict__ bias, int H,
+                                                    int B) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int u = warp >> 2, gate = warp & 3;
+    const int j = cta * 8 + u;
+    const int grow = gate * H + j;
+    const int n_in = n1 + n2, n_tot = n_in + H;
+    const __half* wi = w_ih + static_cast<size_t>(grow) * n_in;
+    const __half* wh = w_hh + static_cast<size_t>(grow) * H;
+    for (int b0 = 0; b0 < B; b0 += 8) {
+        const int nb = min(8, B - b0);
+        const int quads = n_tot >> 2;
+        for (int idx = threadIdx.x; idx < nb * quads; idx += blockDim.x) {
+            const int q = idx / quads, k = (idx - q * quads) << 2;
+            const float* src = k < n1 ? x1 + static_cast<size_t>(b0 + q) * n1 + k
+                                      : (k < n_in ? x2 + static_cast<size_t>(b0 + q) * n2 + (k - n1)
+                                                  : h_in + static_cast<size_t>(b0 + q) * H + (k - n_in));
+            *reinterpret_cast<float4*>(st + q * n_tot + k) = ld_state4(src);
+        }
+        __syncthreads();
+        float acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+        for (int i = lane * 8; i < n_tot; i += 256) {
+            float f[8];
+            if (i < n_in) load8h(wi + i, f); else load8h(wh + (i - n_in), f);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (q < nb) {
+                    const float4 a = *reinterpret_cast<const float4*>(st + q * n_tot + i);
+                    const float4 bb = *reinterpret_cast<const float4*>(st + q * n_tot + i + 4);
+                    acc[q] += f[0] * a.x + f[1] * a.y + f[2] * a.z + f[3] * a.w + f[4] * bb.x + f[5] * bb.y + f[6] * bb.z + f[7] * bb.w;
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float v = warp_sum(acc[q]);
+            if (lane == 0 && q < nb) g_s[u][gate][b0 + q] = v + bias[grow];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 8 * B) {
+        const int uu = threadIdx.x / B, b = threadIdx.x % B;
+        const int jj = cta * 8 + uu;
+        const float ig = sigmoidf_(g_s[uu][0][b]), fg = sigmoidf_(g_s[uu][1][b]);
+        const float gg = tanhf(g_s[uu][2][b]), og = sigmoidf_(g_s[uu][3][b]);
+        const float cn = fg * c[static_cast<size_t>(b) * H + jj] + ig * gg;
+        c[static_cast<size_t>(b) * H + jj] = cn;
+        h_out[static_cast<size_t>(b) * H + jj] = og * tanhf(cn);
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void t2_grid_barrier(unsigned* bar, unsigned target, int* err_flag) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();                       // this CTA's writes are visible before its arrival is
+        atomicAdd(bar, 1u);
+        const long long t0 = clock64();
+        unsigned seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
+            if (seen < target && clock64() - t0 > 4000000000ll) {      // a protocol bug must not hang the box
+                if (err_flag) atomicExch(err_flag, 501);
+                __trap();
+            }
+        } while (seen < target);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024, 1) t2_decoder_persistent_kernel(const T2PersistArgs a) {
+    extern __shared__ float sm[];
+    float (*g_s)[4][64] = reinterpret_cast<float (*)[4][64]>(sm);           // [8 units][4 gates][64 utterances]
+    float* st = sm + 8 * 4 * 64;                                             // staged LSTM inputs, [8][n_in + H]
+    const int G = gridDim.x;
+    unsigned n_bar = 0;
+    const int lstm_blocks = a.H / 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    // prologue: the first step's prenet (later steps get theirs at the end of the previous step's phase D)
+    for (int b = blockIdx.x; b < a.B; b += G)
+        t2_prenet_body(sm, b, a.frame, a.pre_w0, a.pre_w1, a.masks, a.masks + static_cast<size_t>(a.B) * a.P, a.n_mel, a.P, a.x);
+    t2_grid_barrier(a.bar, ++n_bar * G, a.err_flag);
+    for (int i = 0; i < a.n_steps; ++i) {
+        const int step = a.step0 + i;
+        const int cur = step & 1, nxt = cur ^ 1;
+        // A: attention LSTM cell on [prenet out | previous context]
+        for (int vb = blockIdx.x; vb < lstm_blocks; vb += G)
+            t2_lstm_cell_staged(st, g_s, vb, a.x, a.P, a.ctx, a.M, a.ah[cur], a.ah[nxt], a.ac, a.arnn_wih, a.arnn_whh, a.arnn_b, a.H, a.B);
+        t2_grid_barrier(a.bar, ++n_bar * G, a.err_flag);
+        // B: location-sensitive attention, one utterance per CTA
+        for (int b = blockIdx.x; b < a.B; b += G) {
+            t2_attention_body(sm, b, a.ah[nxt], a.memory, a.pmem, a.lens, a.w_query, a.loc_conv, a.loc_dense, a.att_v, a.aw, a.awc,
+                              a.ctx, a.align + static_cast<size_t>(step) * a.B * a.L, a.L, a.H, a.M, a.A, a.NF, a.KL);
+            __syncthreads();
+        }
+        t2_grid_barrier(a.bar, ++n_bar * G, a.err_flag);
+        // C: decoder LSTM cell on [attention hidden | context]
+        for (int vb = blockIdx.x; vb < lstm_blocks; vb += G)
+            t2_lstm_cell_staged(st, g_s, vb, a.ah[nxt], a.H, a.ctx, a.M, a.dh[cur], a.dh[nxt], a.dc, a.drnn_wih, a.drnn_whh, a.drnn_b, a.H, a.B);
+        t2_grid_barrier(a.bar, ++n_bar * G, a.err_flag);
+        // D: mel frame + gate, stop bookkeeping, next prenet — per utterance, no grid barrier in between
+        for (int b = blockIdx.x; b < a.B; b += G) {
+            const float* dhb = a.dh[nxt] + static_cast<size_t>(b) * a.H;
+            const float* cb = a.ctx + static_cast<size_t>(b) * a.M;
+            for (int o = warp; o <= a.n_mel; o += nwarp) {
+                const __half* wr = a.w_proj + static_cast<size_t>(o) * (a.H + a.M);
+                const float d = warp_dot_h<true>(wr, dhb, a.H, lane) + warp_dot_h<true>(wr + a.H, cb, a.M, lane) + a.b_proj[o];
+                if (lane == 0) {
+                    if (o < a.n_mel) {
+                        a.frame[b * a.n_mel + o] = d;
+                        a.frames[(static_cast<size_t>(b) * a.max_steps + step) * a.n_mel + o] = d;
+                    } else {
+                        a.gate[b] = d;
+                        // mel_lens[~finished] += 1; finished |= sigmoid(gate) > thr   (torchaudio:846-849)
+                        if (!a.finished[b]) a.mel_lens[b] += 1;
+                        if (sigmoidf_(d) > a.gate_threshold) a.finished[b] = 1;
+                    }
+                }
+            }
+            __syncthreads();                     // frame[b] complete (this CTA wrote it) before the prenet reads it
+            if (i + 1 < a.n_steps) {
+                const uint8_t* m0 = a.masks + (static_cast<size_t>(i + 1) * 2 + 0) * a.B * a.P;
+                t2_prenet_body(sm, b, a.frame, a.pre_w0, a.pre_w1, m0, m0 + static_cast<size_t>(a.B) * a.P, a.n_mel, a.P, a.x);
+            }
+            __syncthreads();
+        }
+        t2_grid_barrier(a.bar, ++n_bar * G, a.err_flag);
+        // every CTA takes the same stop decision from the same flags
+        bool all = true;
+        for (int b = 0; b < a.B; ++b) all = all && (__ldcg(a.finished + b) != 0);
+        if (all) {
+            if (blockIdx.x == 0 && threadIdx.x == 0 && *a.done_step < 0) *a.done_step = step;
+            if (a.early_stop) break;
+        }
+    }
+}
+
 // frames [B, max_steps, n_mel] fp32 -> channel-last fp16 [B, T, ld] (zero padded channels) for the postnet
 __global__ void t2_frames_to_cl_kernel(const float* __restrict__ frames, int max_steps, int n_mel, int T, int ld,
                                        __half* __restrict__ out) {
@@ -344,6 +557,93 @@ __global__ void t2_finalize_kernel(const float* __restrict__ frames, const float
     }
     if (mel_cl)
         for (int c = n_mel; c < ld; ++c) mel_cl[(static_cast<size_t>(b) * T + t) * ld + c] = __float2half(0.f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// wrapper post-processing on the device (models/tacotron2/networks.py:44-67, 192-206): per utterance
+//   truncate_mel  cut where the attention on the inserted separator first reaches 80 % of its maximum, replicate the
+//                 last kept frame three times
+//   resize_mel    bicubic time resize to int(len / rate) frames (torch.nn.functional.interpolate, mode='bicubic',
+//                 align_corners=False, A = -0.75; the mel-bin axis keeps its size, so the 2-D kernel is 1-D in time)
+// One CTA per utterance; the reference does this in a Python loop with a host sync per utterance.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float cubic1(float x, float A) { return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
+__device__ __forceinline__ float cubic2(float x, float A) { return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; }
+
+__global__ void __launch_bounds__(256) t2_postprocess_kernel(const float* __restrict__ mel, const int* __restrict__ mel_lens,
+                                                             const float* __restrict__ align, const int* __restrict__ cols,
+                                                             double inv_rate, int do_resize, int n_mel, int T, int L, int T_out,
+                                                             float* __restrict__ out, int* __restrict__ out_lens) {
+    __shared__ float red_f[32];
+    __shared__ int red_i[32];
+    __shared__ int s_keep, s_cut, s_new;
+    const int b = blockIdx.x;
+    const int n = min(mel_lens[b], T);
+    const int col = cols ? cols[b] : -1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    if (col >= 0 && n > 0) {
+        const float* ps = align + static_cast<size_t>(b) * T * L + col;
+        float mx = -INFINITY;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, ps[static_cast<size_t>(i) * L]);
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) red_f[warp] = mx;
+        __syncthreads();
+        mx = red_f[0];
+        for (int i = 1; i < nwarp; ++i) mx = fmaxf(mx, red_f[i]);
+        const float thr = 0.8f * mx;
+        int first = n;
+        for (int i = threadIdx.x; i < n; i += blockDim.x)
+            if (ps[static_cast<size_t>(i) * L] >= thr) { first = i; break; }
+        for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+        if (lane == 0) red_i[warp] = first;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int f = red_i[0];
+            for (int i = 1; i < nwarp; ++i) f = min(f, red_i[i]);
+            s_keep = max(f, 1);           // frames kept before the three replicated ones (>= 1: replicate needs a frame)
+            s_cut = s_keep + 3;
+        }
+    } else if (threadIdx.x == 0) {
+        s_keep = n;
+        s_cut = n;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // Nt_new = int(1 / rate * Nt)  (networks.py:62): the same two IEEE double operations as the Python expression
+        int nn = s_cut;
+        if (do_resize) nn = static_cast<int>(inv_rate * static_cast<double>(s_cut));
+        s_new = max(0, min(nn, T_out));
+        out_lens[b] = s_new;
+    }
+    __syncthreads();
+    const int keep = s_keep, cut = s_cut, n_new = s_new;
+    const float* mb = mel + static_cast<size_t>(b) * n_mel * T;
+    float* ob = out + static_cast<size_t>(b) * n_mel * T_out;
+    const bool same = n_new == cut;
+    const float scale = n_new > 0 ? static_cast<float>(cut) / static_cast<float>(n_new) : 0.f;
+    const float A = -0.75f;
+    for (int idx = threadIdx.x; idx < n_mel * T_out; idx += blockDim.x) {
+        const int c = idx / T_out, x = idx - c * T_out;
+        float v = 0.f;
+        if (x < n_new) {
+            const float* row = mb + static_cast<size_t>(c) * T;
+            auto at = [&](int i) {                                // mel_cut with replicate padding, index clamped like ATen
+                i = min(max(i, 0), cut - 1);
+                return row[min(i, keep - 1)];
+            };
+            if (same) {
+                v = at(x);
+            } else {
+                const float src = scale * (static_cast<float>(x) + 0.5f) - 0.5f;
+                const float fl = floorf(src);
+                const int ix = static_cast<int>(fl);
+                const float t = src - fl;
+                const float w0 = cubic2(t + 1.f, A), w1 = cubic1(t, A), w2 = cubic1(1.f - t, A), w3 = cubic2(2.f - t, A);
+                v = at(ix - 1) * w0 + at(ix) * w1 + at(ix + 1) * w2 + at(ix + 2) * w3;
+            }
+        }
+        ob[idx] = v;
+    }
 }
 
 int upload_h16(const float* h, size_t n, __half** d) {
@@ -399,7 +699,7 @@ struct ttsb_tacotron2 {
 namespace {
 
 struct T2State {   // device state of one batch, carved from the caller's state buffer
-    int* lens; int* finished; int* mel_lens; int* done_step; int64_t* spk;
+    int* lens; int* finished; int* mel_lens; int* done_step; unsigned* bar; int64_t* spk;
     float *memory, *pmem, *ah[2], *ac, *dh[2], *dc, *aw, *awc, *ctx, *frame, *x, *gate, *frames, *align;
 };
 
@@ -407,6 +707,7 @@ T2State carve_t2(const ttsb_tacotron2* h, void* p, int B, int L, int max_steps, 
     Carver c(p);
     T2State s;
     s.lens = c.take<int>(B); s.finished = c.take<int>(B); s.mel_lens = c.take<int>(B); s.done_step = c.take<int>(4);
+    s.bar = c.take<unsigned>(4);
     s.spk = c.take<int64_t>(B);
     s.memory = c.take<float>(static_cast<size_t>(B) * L * h->M);
     s.pmem = c.take<float>(static_cast<size_t>(B) * L * h->A);
@@ -479,7 +780,11 @@ int ttsb_tacotron2_create(const ttsb_tensor_t* weights, int n_weights, int devic
         TTSB_REQUIRE(lc->shape[0] == h->NF && lc->shape[1] == 2 && lc->shape[2] == h->KL, "location conv shape");
         TTSB_PROPAGATE(upload_f32(lc->h_data, TensorTable::numel(lc), &h->loc_conv));
         TTSB_GET_TENSOR(ld, tab, A + "location_layer.location_dense.weight", 2);
-        TTSB_PROPAGATE(upload_f32(ld->h_data, TensorTable::numel(ld), &h->loc_dense));
+        TTSB_REQUIRE(ld->shape[0] == h->A && ld->shape[1] == h->NF, "location dense shape");
+        std::vector<float> ldt(static_cast<size_t>(h->A) * h->NF);          // [A][NF] -> [NF][A] (t2_attention_body)
+        for (int a_ = 0; a_ < h->A; ++a_)
+            for (int nf = 0; nf < h->NF; ++nf) ldt[static_cast<size_t>(nf) * h->A + a_] = ld->h_data[static_cast<size_t>(a_) * h->NF + nf];
+        TTSB_PROPAGATE(upload_f32(ldt.data(), ldt.size(), &h->loc_dense));
     }
     {
         TTSB_GET_TENSOR(p0, tab, "decoder.prenet.layers.0.weight", 2);
@@ -571,7 +876,9 @@ int ttsb_tacotron2_encode(ttsb_tacotron2_t* h, const int64_t* d_tokens, const in
 
     TTSB_CHECK_CUDA(cudaMemcpyAsync(st.lens, d_lengths, B * sizeof(int), cudaMemcpyDeviceToDevice, s));
     if (d_speaker_ids) TTSB_CHECK_CUDA(cudaMemcpyAsync(st.spk, d_speaker_ids, B * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
-    t2_embed_kernel<<<B * L, 128, 0, s>>>(d_tokens, h->emb, h->E, xa);
+    TTSB_CHECK_CUDA(cudaMemsetAsync(st.done_step, 0xFF, 4 * sizeof(int), s));       // [0] done step = -1
+    TTSB_CHECK_CUDA(cudaMemsetAsync(st.done_step + 1, 0, sizeof(int), s));           // [1] input status bits
+    t2_embed_kernel<<<B * L, 128, 0, s>>>(d_tokens, h->emb, h->E, h->n_symbol, st.done_step + 1, xa);
     count_launch();
     __half* cur = xa; __half* nxt = xb;
     for (int i = 0; i < 3; ++i) {     // no masking between the convs, exactly like the reference
@@ -589,7 +896,7 @@ int ttsb_tacotron2_encode(ttsb_tacotron2_t* h, const int64_t* d_tokens, const in
     t2_bilstm_kernel<<<dim3(B, 2), 1024, (2 * Hh + 4 * Hh) * sizeof(float), s>>>(xproj, h->enc_whh, st.lens, L, Hh, enc);
     count_launch();
     t2_memory_kernel<<<B * L, 128, h->M * sizeof(float), s>>>(enc, h->spk_emb, st.spk, h->w_mem, L, h->E, h->S, h->A,
-                                                              st.memory, st.pmem);
+                                                              h->num_speakers, st.done_step + 1, st.memory, st.pmem);
     count_launch();
     // decoder state reset (torchaudio:_initialize_decoder_states, _get_go_frame)
     float* zero_f[] = {st.ah[0], st.ah[1], st.ac, st.dh[0], st.dh[1], st.dc};
@@ -600,7 +907,6 @@ int ttsb_tacotron2_encode(ttsb_tacotron2_t* h, const int64_t* d_tokens, const in
     TTSB_CHECK_CUDA(cudaMemsetAsync(st.frame, 0, static_cast<size_t>(B) * h->n_mel * sizeof(float), s));
     TTSB_CHECK_CUDA(cudaMemsetAsync(st.finished, 0, B * sizeof(int), s));
     TTSB_CHECK_CUDA(cudaMemsetAsync(st.mel_lens, 0, B * sizeof(int), s));
-    TTSB_CHECK_CUDA(cudaMemsetAsync(st.done_step, 0xFF, 4 * sizeof(int), s));
     TTSB_CHECK_CUDA(cudaGetLastError());
     return 0;
     });
@@ -610,7 +916,8 @@ int ttsb_tacotron2_encode(ttsb_tacotron2_t* h, const int64_t* d_tokens, const in
  * prenet dropout. h_done_step (host, optional): after the call (synchronises the stream) receives the first
  * step index at which every utterance had finished, or -1. */
 int ttsb_tacotron2_decode(ttsb_tacotron2_t* h, int B, int L, int max_steps, int step0, int n_steps,
-                          const uint8_t* d_masks, float gate_threshold, void* d_state, int* h_done_step, void* stream_) {
+                          const uint8_t* d_masks, float gate_threshold, int early_stop, void* d_state, int* h_done_step,
+                          void* stream_) {
     return guarded_call([&]() -> int {
     TTSB_REQUIRE(h && d_masks && d_state, "null argument");
     TTSB_REQUIRE(step0 >= 0 && n_steps > 0 && step0 + n_steps <= max_steps, "step range");
@@ -619,6 +926,48 @@ int ttsb_tacotron2_decode(ttsb_tacotron2_t* h, int B, int L, int max_steps, int 
     T2State st = carve_t2(h, d_state, B, L, max_steps, nullptr);
     const int H = h->H, M = h->M, P = h->P;
     const size_t att_smem = (h->A + 2 * (L + h->KL) + L + 32) * sizeof(float);
+    static const int want_persistent = getenv("TTSB_T2_PERSISTENT") ? atoi(getenv("TTSB_T2_PERSISTENT")) : 1;
+    if (want_persistent) {
+        // one cooperative launch for the whole chunk (t2_decoder_persistent_kernel)
+        T2PersistArgs a;
+        a.B = B; a.L = L; a.H = H; a.M = M; a.P = P; a.A = h->A; a.NF = h->NF; a.KL = h->KL; a.n_mel = h->n_mel;
+        a.max_steps = max_steps; a.step0 = step0; a.n_steps = n_steps; a.early_stop = early_stop ? 1 : 0;
+        a.gate_threshold = gate_threshold;
+        a.masks = d_masks; a.lens = st.lens; a.memory = st.memory; a.pmem = st.pmem;
+        a.ah[0] = st.ah[0]; a.ah[1] = st.ah[1]; a.ac = st.ac; a.dh[0] = st.dh[0]; a.dh[1] = st.dh[1]; a.dc = st.dc;
+        a.aw = st.aw; a.awc = st.awc; a.ctx = st.ctx; a.frame = st.frame; a.x = st.x; a.gate = st.gate; a.frames = st.frames;
+        a.align = st.align; a.finished = st.finished; a.mel_lens = st.mel_lens; a.done_step = st.done_step; a.bar = st.bar;
+        ConvRuntime rt;
+        TTSB_PROPAGATE(get_conv_runtime(0, rt));
+        a.err_flag = rt.err_flag;
+        a.pre_w0 = h->pre_w0; a.pre_w1 = h->pre_w1; a.arnn_wih = h->arnn_wih; a.arnn_whh = h->arnn_whh;
+        a.drnn_wih = h->drnn_wih; a.drnn_whh = h->drnn_whh; a.w_query = h->w_query; a.w_proj = h->w_proj;
+        a.arnn_b = h->arnn_b; a.drnn_b = h->drnn_b; a.loc_conv = h->loc_conv; a.loc_dense = h->loc_dense; a.att_v = h->att_v;
+        a.b_proj = h->b_proj;
+        const size_t lstm_smem = (8 * 4 * 64 + static_cast<size_t>(8) * (std::max(P, H) + M + H)) * sizeof(float);
+        const size_t smem = std::max({att_smem, static_cast<size_t>(h->n_mel + P) * sizeof(float), lstm_smem});
+        static PerDeviceOnce configured;
+        if (!configured.here()) {
+            TTSB_CHECK_CUDA(cudaFuncSetAttribute(t2_decoder_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            configured.here() = true;
+        }
+        TTSB_REQUIRE(smem <= 200 * 1024 && H % 8 == 0, "persistent decoder: shared-memory plan");
+        int per_sm = 0;
+        TTSB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, t2_decoder_persistent_kernel, 1024, smem));
+        TTSB_REQUIRE(per_sm >= 1, "persistent decoder does not fit on an SM");
+        // one CTA per SM; one pass over the LSTM's H/8 eight-unit blocks when the device has that many SMs
+        const int grid = std::min(num_sms(), std::max(H / 8, B));
+        TTSB_CHECK_CUDA(cudaMemsetAsync(st.bar, 0, 4 * sizeof(unsigned), s));
+        void* kargs[] = {&a};
+        TTSB_CHECK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(t2_decoder_persistent_kernel), dim3(grid), dim3(1024),
+                                                    kargs, smem, s));
+        count_launch();
+        if (h_done_step) {
+            TTSB_CHECK_CUDA(cudaMemcpyAsync(h_done_step, st.done_step, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+            TTSB_CHECK_CUDA(cudaStreamSynchronize(s));
+        }
+        return 0;
+    }
     for (int i = 0; i < n_steps; ++i) {
         const int step = step0 + i;
         const int cur = step & 1, nxt = cur ^ 1;
@@ -639,9 +988,26 @@ int ttsb_tacotron2_decode(ttsb_tacotron2_t* h, int B, int L, int max_steps, int 
     }
     TTSB_CHECK_CUDA(cudaGetLastError());
     if (h_done_step) {
-        TTSB_CHECK_CUDA(cudaMemcpyAsync(h_done_step, st.done_step, sizeof(int), cudaMemcpyDeviceToHost, s));
+        TTSB_CHECK_CUDA(cudaMemcpyAsync(h_done_step, st.done_step, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
         TTSB_CHECK_CUDA(cudaStreamSynchronize(s));
     }
+    return 0;
+    });
+}
+
+int ttsb_tacotron2_postprocess(const float* d_mel, const int32_t* d_mel_lens, const float* d_align, const int32_t* d_cols,
+                               double rate, int B, int n_mel, int T, int L, int T_out, float* d_out, int32_t* d_out_lens,
+                               void* stream_) {
+    return guarded_call([&]() -> int {
+    TTSB_REQUIRE(d_mel && d_mel_lens && d_out && d_out_lens, "null argument");
+    TTSB_REQUIRE(B > 0 && n_mel > 0 && T > 0 && T_out > 0, "empty batch");
+    TTSB_REQUIRE(d_cols == nullptr || d_align != nullptr, "truncation needs the alignments");
+    TTSB_REQUIRE(rate > 0.0, "speed rate must be positive");
+    const int do_resize = rate != 1.0 ? 1 : 0;
+    t2_postprocess_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream_)>>>(d_mel, d_mel_lens, d_align, d_cols, 1.0 / rate,
+                                                                           do_resize, n_mel, T, L, T_out, d_out, d_out_lens);
+    count_launch();
+    TTSB_CHECK_CUDA(cudaGetLastError());
     return 0;
     });
 }

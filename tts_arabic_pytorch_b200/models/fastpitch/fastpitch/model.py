@@ -187,10 +187,12 @@ class FastPitch(nn.Module):
     # ------------------------------------------------------------------ reference API
     @torch.no_grad()
     def infer(self, inputs, pace=1.0, dur_tgt=None, pitch_tgt=None, energy_tgt=None, pitch_transform=None,
-              max_duration=75, speaker=0, return_channel_last=False, taps=None):
+              max_duration=75, speaker=0, return_channel_last=False, taps=None, frame_len_hook=None):
         """Same contract as the reference (model.py:351-409): returns
         (mel_out [B,80,T], dec_lens [B] int64, dur_pred [B,L], pitch_pred [B,1,L], energy_pred [B,L] | None).
-        With return_channel_last=True a 6th item is appended: the fp16 [B,T,128] mel for the vocoder."""
+        With return_channel_last=True a 6th item is appended: the fp16 [B,T,128] mel for the vocoder.
+        frame_len_hook (sharded batches, parallel.synthesize): maps this batch's max(dec_lens) to the frame count to
+        decode with (>= it), so that a shard can keep the padded-frame condition of the global batch."""
         device = self.proj.weight.device
         if device.type != 'cuda':
             raise RuntimeError('tts_arabic_pytorch_b200 has no CPU path: move the model to a CUDA device')
@@ -256,6 +258,8 @@ class FastPitch(nn.Module):
                 raise ValueError('padding ids must be trailing and every utterance non-empty')
             if T <= 0:
                 raise RuntimeError('all predicted durations are zero')
+            if frame_len_hook is not None:
+                T = max(T, int(frame_len_hook(T)))
             nb = lib.ttsb_fastpitch_workspace_bytes(handle, B, L, T)
             ws = self._ws.get(nb, device)
             mel = torch.empty(B, self.cfg['n_mel_channels'], T, **f32)

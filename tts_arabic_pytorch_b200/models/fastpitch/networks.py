@@ -92,11 +92,14 @@ class FastPitch(_FastPitch):
     # ------------------------------------------------------------------ ids -> mel (batch core)
     @torch.inference_mode()
     def _infer_ids(self, id_list: List[torch.Tensor], speed, speaker_id, pitch_transform, dur_tgt, pitch_tgt,
-                   energy_tgt, max_duration, channel_last=False):
+                   energy_tgt, max_duration, channel_last=False, pad_to: int = 0, frame_len_hook=None):
+        """pad_to / frame_len_hook: a shard of a larger batch keeps that batch's padding condition (parallel.py)."""
         padded, _, inverse = text_collate_fn(id_list)
+        if pad_to > padded.shape[1]:
+            padded = torch.nn.functional.pad(padded, (0, pad_to - padded.shape[1]))
         out = self.infer(padded.to(self.device), pace=speed, speaker=speaker_id, dur_tgt=dur_tgt, pitch_tgt=pitch_tgt,
                          energy_tgt=energy_tgt, pitch_transform=pitch_transform, max_duration=max_duration,
-                         return_channel_last=channel_last)
+                         return_channel_last=channel_last, frame_len_hook=frame_len_hook)
         return out, inverse
 
     @torch.inference_mode()
@@ -158,15 +161,19 @@ class FastPitch2Wave(nn.Module):
     # ------------------------------------------------------------------ ids -> waveforms (batch core)
     @torch.inference_mode()
     def synthesize_ids(self, id_list: List[torch.Tensor], speed=1., speaker_id=0, denoise=0., pitch_transform=None,
-                       max_duration=75, to_cpu=True):
+                       max_duration=75, to_cpu=True, pad_to: int = 0, frame_len_hook=None, return_padded=False):
         """Core used by every tts_* method: padded FastPitch batch -> ONE masked vocoder call ->
         (optional) batched denoiser -> single D2H copy. Returns (list of 1-D waveforms in input order,
         list of [80,T_i] mels)."""
         (mel, dec_lens, _, _, _, mel_cl), inverse = self.model._infer_ids(
-            id_list, speed, speaker_id, pitch_transform, None, None, None, max_duration, channel_last=True)
+            id_list, speed, speaker_id, pitch_transform, None, None, None, max_duration, channel_last=True,
+            pad_to=pad_to, frame_len_hook=frame_len_hook)
         wav = self.vocoder.run(mel_cl=mel_cl, lens=dec_lens)              # [B, T_max*hop]
         if denoise > 0:
             wav = self.denoiser.denoise_batch(wav, dec_lens * self.vocoder.hop, denoise)
+        if return_padded:
+            # device-resident form for parallel.synthesize: padded waveforms in SORTED order + what undoes the sort
+            return wav, dec_lens * self.vocoder.hop, inverse, mel
         lens = dec_lens.tolist()
         hop = self.vocoder.hop
         order = inverse.tolist()

@@ -4,15 +4,17 @@
   Tacotron2(checkpoint, n_symbol, decoder_max_step, arabic_in, vowelizer)   :71-253
   Tacotron2Wave(model_sd_path, vocoder_sd, vocoder_config, vowelizer, arabic_in, n_symbol)  :256-426
 The acoustic model runs through the C ABI (tacotron2_ms.Tacotron2MS.infer); the alignment-based mel
-truncation and the bicubic speed resize stay host-side torch ops, as in the reference (SURVEY.md §8f
-rank 3); the vocoder runs once per batch over the length-masked padded mels.
+truncation and the bicubic speed resize of a whole batch are ONE kernel launch and one host read of the
+new lengths (ttsb_tacotron2_postprocess) instead of the reference's per-utterance Python loop with a host
+sync each; `truncate_mel` / `resize_mel` remain as the module-level functions the
+reference exports. The vocoder runs once per batch over the length-masked padded mels.
 """
 from typing import List, Optional, Union
 
 import torch
 import torch.nn as nn
 
-from ... import text
+from ... import _lib, text
 from ...text.symbols import EOS_TOKENS, SEPARATOR_TOKEN
 from ...utils import get_basic_config
 from ...vocoder import load_hifigan
@@ -41,6 +43,45 @@ def resize_mel(mel: torch.Tensor, rate: Union[int, float] = 1.0, mode: str = 'bi
     if n_new == n_t:
         return mel
     return torch.nn.functional.interpolate(mel[None, None, ...], (n_f, n_new), mode=mode)[0, 0]
+
+
+def postprocess_batch(mel: torch.Tensor, mel_lens, align: Optional[torch.Tensor], cols: Optional[List[int]],
+                      speed: Union[int, float, None]) -> List[torch.Tensor]:
+    """mel [B,F,T] (+ lengths, alignments [B,T,L]) -> list of [F,T_b'] mels: utterance b is truncated on alignment
+    column cols[b] (< 0 or None: not truncated) and then resized by `speed` (None: not resized), exactly as
+    `truncate_mel` then `resize_mel`. On a CUDA tensor: one launch for the batch + one host read of the new lengths."""
+    B, F, T = mel.shape
+    lens = [int(x) for x in (mel_lens.tolist() if torch.is_tensor(mel_lens) else mel_lens)]
+    if speed is None and (cols is None or all(c < 0 for c in cols)):
+        return [mel[b, :, :lens[b]] for b in range(B)]
+    if not mel.is_cuda:
+        # module-level reference functions on host tensors (the wrapper unit tests drive them with a CPU stand-in model)
+        out = []
+        for b in range(B):
+            m = mel[b, :, :lens[b]]
+            if cols is not None and cols[b] >= 0:
+                m = truncate_mel(m, align[b, :lens[b], cols[b]])
+            if speed is not None:
+                m = resize_mel(m, rate=speed)
+            out.append(m)
+        return out
+    lib = _lib.load()
+    dev = mel.device
+    rate = 1.0 if speed is None else float(speed)
+    t_cap = int(1.0 / rate * (max(lens) + 3)) + 1 if rate != 1.0 else max(lens) + 3
+    mel = mel.to(torch.float32).contiguous()
+    lens_d = torch.tensor(lens, dtype=torch.int32, device=dev)
+    cols_d = None if cols is None else torch.tensor(cols, dtype=torch.int32, device=dev)
+    align_c = None if (align is None or cols is None) else align.to(torch.float32).contiguous()
+    L = 0 if align_c is None else align_c.shape[2]
+    out = torch.empty(B, F, t_cap, dtype=torch.float32, device=dev)
+    out_lens = torch.empty(B, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ttsb_tacotron2_postprocess(_lib.ptr(mel), _lib.ptr(lens_d), _lib.ptr(align_c), _lib.ptr(cols_d), rate,
+                                                  B, F, T, L, t_cap, _lib.ptr(out), _lib.ptr(out_lens),
+                                                  _lib.current_stream(dev)))
+    new = out_lens.tolist()                 # the one host read of the batch
+    return [out[b, :, :new[b]] for b in range(B)]
 
 
 class Tacotron2(Tacotron2MS):
@@ -96,12 +137,8 @@ class Tacotron2(Tacotron2MS):
                      postprocess_mel: bool = True):
         ids, process = self._prepare(utterance, vowelizer, postprocess_mel)
         mel, _, align = self.infer(ids[None].to(self.device), torch.LongTensor([speaker_id]).to(self.device))
-        mel = mel[0]
-        if process:
-            mel = truncate_mel(mel, align[0, :, -self.n_eos - 1])
-        if speed is not None:
-            mel = resize_mel(mel, rate=speed)
-        return mel   # [F, T]
+        col = align.shape[2] - self.n_eos - 1 if process else -1
+        return postprocess_batch(mel, [mel.shape[2]], align, [col], speed)[0]   # [F, T]
 
     @torch.inference_mode()
     def ttmel_batch(self, batch: List[str], speaker_id: int = 0, speed: Union[int, float, None] = None, vowelizer=None,
@@ -110,17 +147,14 @@ class Tacotron2(Tacotron2MS):
         padded, lens_sorted, inverse = text_collate_fn([p[0] for p in prepared])
         sids = torch.full((len(batch),), speaker_id, dtype=torch.long)
         mel, mel_lens, align = self.infer(padded.to(self.device), sids.to(self.device), lens_sorted.to(self.device))
-        mel_lens = mel_lens.tolist()
         lens_sorted = lens_sorted.tolist()
-        out = []
-        for i, row in enumerate(inverse.tolist()):
-            m = mel[row, :, :mel_lens[row]]
+        order = inverse.tolist()
+        cols = [-1] * len(batch)               # per ROW of the sorted batch
+        for i, row in enumerate(order):
             if prepared[i][1]:
-                m = truncate_mel(m, align[row, :mel_lens[row], lens_sorted[row] - self.n_eos - 1])
-            if speed is not None:
-                m = resize_mel(m, rate=speed)
-            out.append(m)
-        return out
+                cols[row] = lens_sorted[row] - self.n_eos - 1
+        done = postprocess_batch(mel, mel_lens, align, cols, speed)
+        return [done[row] for row in order]
 
     def ttmel(self, text_input: Union[str, List[str]], speaker_id: int = 0, speed: Union[int, float, None] = None,
               batch_size: int = 8, vowelizer=None, postprocess_mel: bool = True):

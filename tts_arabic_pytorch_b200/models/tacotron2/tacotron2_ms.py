@@ -73,7 +73,8 @@ def parameter_spec(n_symbol=40, num_speakers=40, speaker_embedding_dim=128, n_me
 
 
 class Tacotron2MS(nn.Module):
-    STEP_CHUNK = 32      # decoder steps between two polls of the "all finished" flag
+    MAX_GROUP = 64       # utterances per launch train (t2_lstm_cell_body's shared staging)
+    STEP_CHUNK = 64      # decoder steps per cooperative launch = between two host reads of the "all finished" flag
 
     def __init__(self, mask_padding: bool = False, n_mels: int = 80, n_symbol: int = 148, n_frames_per_step: int = 1,
                  num_speakers=40, speaker_embedding_dim=128, decoder_max_step: int = 2000,
@@ -152,6 +153,22 @@ class Tacotron2MS(nn.Module):
         lib = _lib.load()
         tokens = tokens.to(device=device, dtype=torch.int64).contiguous()
         B, L = tokens.shape
+        if B > self.MAX_GROUP:
+            # the LSTM-cell kernels stage gate pre-activations for at most 64 utterances: larger batches run as groups
+            # (utterances are independent; frames beyond an utterance's own mel_lengths are not part of the contract)
+            parts = []
+            for k in range(0, B, self.MAX_GROUP):
+                sl = slice(k, k + self.MAX_GROUP)
+                parts.append(self.infer(tokens[sl], None if speaker_ids is None else speaker_ids[sl],
+                                        None if lengths is None else lengths[sl],
+                                        None if prenet_masks is None else prenet_masks[:, :, sl],
+                                        return_channel_last))
+            t_max = max(p[0].shape[2] for p in parts)
+
+            def cat(i, dim, width):
+                return torch.cat([torch.nn.functional.pad(p[i], width(t_max - p[0].shape[2])) for p in parts], dim=0)
+            out = (cat(0, 0, lambda d: (0, d)), torch.cat([p[1] for p in parts]), cat(2, 0, lambda d: (0, 0, 0, d)))
+            return out + (cat(3, 0, lambda d: (0, 0, 0, d)),) if return_channel_last else out
         if lengths is None:
             lengths = torch.full((B,), L, dtype=torch.int32, device=device)
         lengths = lengths.to(device=device, dtype=torch.int32).contiguous()
@@ -166,7 +183,7 @@ class Tacotron2MS(nn.Module):
             ws = self._ws.get(lib.ttsb_tacotron2_workspace_bytes(handle, B, L, 0), device)
             _lib.check(lib.ttsb_tacotron2_encode(handle, _lib.ptr(tokens), _lib.ptr(lengths), _lib.ptr(speaker_ids), B, L,
                                                  max_steps, _lib.ptr(state), _lib.ptr(ws), ws.numel(), stream))
-            done = ctypes.c_int(-1)
+            done = (ctypes.c_int * 2)(-1, 0)
             step = 0
             while step < max_steps:
                 n = min(self.STEP_CHUNK, max_steps - step)
@@ -175,12 +192,17 @@ class Tacotron2MS(nn.Module):
                 else:
                     masks = prenet_masks[step:step + n].to(device=device, dtype=torch.uint8).contiguous()
                 _lib.check(lib.ttsb_tacotron2_decode(handle, B, L, max_steps, step, n, _lib.ptr(masks),
-                                                     float(self.gate_threshold), _lib.ptr(state), ctypes.byref(done), stream))
+                                                     float(self.gate_threshold), int(bool(self.decoder_early_stopping)),
+                                                     _lib.ptr(state), done, stream))
+                if done[1] & 1:
+                    raise IndexError('token id out of range [0, %d)' % self.embedding.weight.shape[0])
+                if done[1] & 4:
+                    raise IndexError('speaker id out of range [0, %d)' % self.num_speakers)
                 step += n
-                if self.decoder_early_stopping and done.value >= 0:
+                if self.decoder_early_stopping and done[0] >= 0:
                     break
-            if self.decoder_early_stopping and done.value >= 0:
-                T = done.value + 1
+            if self.decoder_early_stopping and done[0] >= 0:
+                T = done[0] + 1
             else:
                 T = step
                 if T == self.decoder_max_step:

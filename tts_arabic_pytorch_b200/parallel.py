@@ -1,9 +1,22 @@
 """Multi-GPU layer: utterances are independent end to end, so a batch shards across ranks with no
-data-path collective; the only exchange is the final delivery of waveforms.
+bulk data-path collective; the only bulk exchange is the final delivery of waveforms.
 
 One process per GPU (torch.distributed, NCCL over NVLink on the GPU box, gloo in CPU tests).
   shard_utterances   length-balanced "snake" deal of a length-sorted utterance list
+  plan_shards        + the padding each shard needs to keep the GLOBAL batch's padded-position condition
+  synthesize         the product entry point: FastPitch2Wave over a sharded utterance list, results on `dst`
   gather_waveforms   all_gather of sample counts, then one padded gather to the destination rank
+  HostSharedBuffer   single-node delivery: every rank copies its rows device -> host shared memory over its own
+                     PCIe link, the destination rank maps the same segment (no rank-0 D2H of everybody's samples)
+
+Why a shard is not simply "its own batch": the reference runs ONE padded batch (models/fastpitch/networks.py:140-195) and
+FastPitch is not batch-invariant — PositionwiseConvFF and the predictors stack convolutions without a mask in between
+(transformer.py:83-85, model.py:129-133), so an utterance's last valid positions depend on whether at least one padded
+position follows them (any number >= 1 gives the same values: padded inputs are exactly zero). In a shard the longest
+utterance would lose that padded position, so `plan_shards` gives every shard whose longest utterance is shorter than the
+global maximum ONE extra padded token column, and `synthesize` does the same in the frame domain with one 4-byte
+all-reduce(max) of the frame count between the duration stage and the decoder — the only data-dependent exchange of the
+path. With both, the sharded result equals the single-batch result bit for bit (tests/test_gpu_parallel.py).
 """
 from typing import List, Optional, Sequence, Tuple
 
@@ -21,6 +34,162 @@ def shard_utterances(lengths: Sequence[int], world_size: int) -> List[List[int]]
         rank = off if rnd % 2 == 0 else world_size - 1 - off
         shards[rank].append(idx)
     return shards
+
+
+def plan_shards(lengths: Sequence[int], world_size: int) -> Tuple[List[List[int]], List[int]]:
+    """(shards, pad_to): shards as `shard_utterances`; pad_to[r] = token columns rank r pads its batch to, i.e. its own
+    maximum length plus one column when that maximum is below the global one (see the module docstring)."""
+    shards = shard_utterances(lengths, world_size)
+    l_max = max(int(n) for n in lengths) if len(lengths) else 0
+    pad_to = []
+    for idxs in shards:
+        own = max((int(lengths[i]) for i in idxs), default=0)
+        pad_to.append(own + 1 if 0 < own < l_max else own)
+    return shards, pad_to
+
+
+class HostSharedBuffer:
+    """A POSIX shared-memory segment viewed as an fp32 [rows, cols] tensor by every rank of ONE node, page-locked in each
+    process so that device -> host copies into it run at full PCIe speed from every GPU at once."""
+
+    def __init__(self, name: str, rows: int, cols: int, create: bool):
+        from multiprocessing import shared_memory
+        nbytes = max(4, rows * cols * 4)
+        self.shm = shared_memory.SharedMemory(name=name, create=create, size=nbytes if create else 0)
+        import numpy as np
+        self.array = np.ndarray((rows, cols), dtype=np.float32, buffer=self.shm.buf)
+        self.tensor = torch.from_numpy(self.array)
+        self.registered = False
+        if torch.cuda.is_available():
+            r = torch.cuda.cudart().cudaHostRegister(self.tensor.data_ptr(), self.tensor.numel() * 4, 0)
+            self.registered = int(r) == 0
+        self.owner = create
+
+    def close(self):
+        if self.registered:
+            torch.cuda.cudart().cudaHostUnregister(self.tensor.data_ptr())
+            self.registered = False
+        self.tensor = None
+        self.array = None
+        try:
+            self.shm.close()
+            if self.owner:
+                self.shm.unlink()
+        except Exception:
+            pass
+
+
+@torch.inference_mode()
+def synthesize(model, id_list: List[torch.Tensor], speed=1., speaker_id=0, denoise=0., pitch_transform=None,
+               max_duration=75, dst: int = 0, group=None, deliver: str = 'nccl', return_stats: bool = False):
+    """FastPitch2Wave.synthesize_ids over the ranks of `group`: every rank passes the SAME utterance list (token ids are
+    tiny), synthesizes its own shard and delivers the waveforms to rank `dst`, which returns the list of 1-D waveforms in
+    input order (None elsewhere). deliver = 'nccl' (padded gather over NCCL/NVLink; rows stay on dst's device),
+    'nccl_host' (the same + one device -> host copy on dst), 'host_shm' (single node: every rank copies its rows into one
+    shared pinned host segment over its own PCIe link; dst returns CPU tensors)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    lengths = [int(x.numel()) for x in id_list]
+    shards, pad_to = plan_shards(lengths, world)
+    mine = shards[rank]
+    dev = model.device
+
+    def frame_len_hook(t_local: int) -> int:
+        # the frame-domain twin of pad_to: one extra padded frame when this shard's longest mel is shorter than the
+        # global longest (4-byte all-reduce; the reference's single batch knows the global maximum by construction)
+        if world == 1:
+            return t_local
+        t = torch.tensor([t_local], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        return t_local + 1 if t_local < int(t[0]) else t_local
+
+    if mine:
+        wav, n_samples, inverse, _ = model.synthesize_ids([id_list[i] for i in mine], speed, speaker_id, denoise,
+                                                          pitch_transform, max_duration, to_cpu=False,
+                                                          pad_to=pad_to[rank], frame_len_hook=frame_len_hook,
+                                                          return_padded=True)
+        # sorted-batch row of the shard's k-th utterance
+        rows = inverse.to(dev)
+        wav = wav.index_select(0, rows)
+        n_samples = n_samples.index_select(0, rows)
+    else:
+        frame_len_hook(0)                     # keep the collective matched
+        wav = torch.zeros(0, 1, dtype=torch.float32, device=dev)
+        n_samples = torch.zeros(0, dtype=torch.int64, device=dev)
+    stats = {'frames': int(n_samples.sum()) // max(1, model.vocoder.hop), 'utterances': len(mine)}
+
+    if world == 1:
+        if deliver != 'nccl':
+            # one D2H copy of the padded batch into pinned memory (the same staging FastPitch2Wave.synthesize_ids uses)
+            host = torch.empty(wav.shape, dtype=wav.dtype, pin_memory=True)
+            host.copy_(wav, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            wav = host
+        out = [wav[k, :int(n)] for k, n in enumerate(n_samples.tolist())]
+        res = unshard([out], shards)
+        return (res, stats) if return_stats else res
+
+    if deliver == 'host_shm':
+        meta = torch.tensor([wav.shape[0], wav.shape[1]], dtype=torch.int64, device=dev)
+        metas = [torch.empty_like(meta) for _ in range(world)]
+        dist.all_gather(metas, meta, group=group)
+        rows_of = [int(m[0]) for m in metas]
+        n_max = max(int(m[1]) for m in metas)
+        total = sum(rows_of)
+        name_t = torch.zeros(1, dtype=torch.int64, device=dev)
+        if rank == dst:
+            import os
+            name_t[0] = int.from_bytes(os.urandom(6), 'little')
+        dist.broadcast(name_t, src=dst, group=group)
+        name = 'ttsb_%x' % int(name_t[0])
+        buf = HostSharedBuffer(name, total, n_max, create=True) if rank == dst else None
+        cnt_all = [torch.empty(r, dtype=torch.int64, device=dev) for r in rows_of]
+        dist.all_gather(cnt_all, n_samples, group=group) if len(set(rows_of)) == 1 else _all_gather_ragged(cnt_all, n_samples, group)
+        dist.barrier(group=group)             # the segment exists
+        if rank != dst:
+            buf = HostSharedBuffer(name, total, n_max, create=False)
+        r0 = sum(rows_of[:rank])
+        if wav.shape[0]:
+            buf.tensor[r0:r0 + wav.shape[0], :wav.shape[1]].copy_(wav, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        dist.barrier(group=group)             # every rank's rows are in host memory
+        res = None
+        if rank == dst:
+            per_rank, at = [], 0
+            for r in range(world):
+                cnt = cnt_all[r].tolist()
+                per_rank.append([buf.tensor[at + k, :int(n)].clone() for k, n in enumerate(cnt)])
+                at += rows_of[r]
+            res = unshard(per_rank, shards)
+        dist.barrier(group=group)
+        buf.close()
+        return (res, stats) if return_stats else res
+
+    got = gather_waveforms(wav, n_samples, dst=dst, group=group)
+    res = None
+    if rank == dst:
+        ws, cs = got
+        per_rank = []
+        for w, c in zip(ws, cs):
+            if deliver == 'nccl_host':
+                host = torch.empty(w.shape, dtype=w.dtype, pin_memory=True)
+                host.copy_(w, non_blocking=True)
+                torch.cuda.current_stream(dev).synchronize()
+                w = host
+            per_rank.append([w[k, :int(n)] for k, n in enumerate(c.tolist())])
+        res = unshard(per_rank, shards)
+    return (res, stats) if return_stats else res
+
+
+def _all_gather_ragged(outs: List[torch.Tensor], mine: torch.Tensor, group=None):
+    """all_gather for per-rank tensors of different lengths (pad to the longest, trim on arrival)."""
+    n_max = max(int(o.numel()) for o in outs)
+    pad = torch.zeros(n_max, dtype=mine.dtype, device=mine.device)
+    pad[:mine.numel()] = mine
+    bufs = [torch.empty_like(pad) for _ in outs]
+    dist.all_gather(bufs, pad, group=group)
+    for o, b in zip(outs, bufs):
+        o.copy_(b[:o.numel()])
 
 
 def gather_waveforms(wav: torch.Tensor, n_samples: torch.Tensor, dst: int = 0,

@@ -99,6 +99,7 @@ class Generator(nn.Module):
 
     # ------------------------------------------------------------------ C ABI plumbing
     def _drop_handle(self):
+        self.__dict__.pop('_graphs', None)     # captured graphs hold the handle's device buffers
         if getattr(self, '_handle', None) is not None:
             _lib.load().ttsb_hifigan_destroy(self._handle)
         self._handle = None
@@ -167,6 +168,43 @@ class Generator(nn.Module):
                                                 _lib.ptr(wav), _lib.ptr(ws), nbytes, _lib.current_stream(device)))
         del src
         return wav
+
+    # ------------------------------------------------------------------ CUDA graphs (small batches)
+    def capture_graph(self, mel, lens=None):
+        """Captures the generator's launch train for this input SHAPE into a CUDA graph and returns `replay(mel=None,
+        lens=None) -> wav [B, T*hop]`: one graph launch instead of ~62 kernel launches, which is what a single utterance is
+        bound by (BASELINE config 2: the launches of a 512-frame utterance take longer to issue than to run).
+        `replay` copies a new mel (same shape) into the captured input buffer first; the returned tensor is the graph's
+        static output and is overwritten by the next replay. One graph per (B, T, with-lens) is kept."""
+        device = self._device()
+        if device.type != 'cuda':
+            raise RuntimeError('tts_arabic_pytorch_b200 has no CPU path: move the vocoder to a CUDA device')
+        if mel.dim() == 2:
+            mel = mel[None]
+        key = (tuple(mel.shape), lens is not None)
+        cache = self.__dict__.setdefault('_graphs', {})
+        if key not in cache:
+            static_mel = mel.to(device=device, dtype=torch.float32).contiguous().clone()
+            static_lens = None if lens is None else lens.to(device=device, dtype=torch.int32).contiguous().clone()
+            self.run(mel_f32=static_mel, lens=static_lens)      # warm-up outside capture: handle, workspace, attributes
+            torch.cuda.synchronize(device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_wav = self.run(mel_f32=static_mel, lens=static_lens)
+            cache[key] = (graph, static_mel, static_lens, static_wav)
+        graph, static_mel, static_lens, static_wav = cache[key]
+
+        def replay(new_mel=None, new_lens=None):
+            if new_mel is not None:
+                static_mel.copy_(new_mel if new_mel.dim() == 3 else new_mel[None], non_blocking=True)
+            if new_lens is not None and static_lens is not None:
+                static_lens.copy_(new_lens, non_blocking=True)
+            graph.replay()
+            return static_wav
+        return replay
+
+    def _drop_graphs(self):
+        self.__dict__.pop('_graphs', None)
 
     def forward(self, x, lens=None):
         if x.dim() == 2:                       # [80,T] -> [1, 256T]   (hifigan/models.py:111-127)
