@@ -92,9 +92,11 @@ size_t ttsb_hifigan_workspace_bytes(const ttsb_hifigan_t* h, int B, int T);
  * reference layout) or d_mel_cl ([B,T,128] fp16 channel-last, rows >= len zero) is non-NULL.
  * d_lens [B] int32 frames per utterance (NULL = all T): every layer treats frames beyond an
  * utterance's length as the zero padding the reference's per-utterance call would see
- * (models/fastpitch/networks.py:340-345). d_wav: [B, T*hop] fp32, zero beyond len*hop. */
+ * (models/fastpitch/networks.py:340-345). d_wav: [B, T*hop] fp32, zero beyond len*hop.
+ * h_lens (optional): a HOST copy of d_lens. With it the batch is processed in chunks that each run at their own
+ * longest utterance instead of T, so the padding of a mixed-length batch is not computed (results are identical). */
 int ttsb_hifigan_forward(ttsb_hifigan_t* h, const float* d_mel_f32, const void* d_mel_cl,
-                         const int32_t* d_lens, int B, int T, float* d_wav, void* d_workspace,
+                         const int32_t* d_lens, const int32_t* h_lens, int B, int T, float* d_wav, void* d_workspace,
                          size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -144,8 +146,8 @@ int ttsb_fastpitch_encode(ttsb_fastpitch_t* h, const int64_t* d_ids, int B, int 
 int ttsb_fastpitch_read_enc_out(ttsb_fastpitch_t* h, int B, int L, const void* d_state, void* d_enc_out, void* stream);
 /* d_pitch_in [B,L]: pitch track to embed (predicted, transformed or target). d_energy_tgt [B,L] or
  * NULL (predict). d_dur_tgt [B,L] or NULL (use exp(log_dur)-1). Outputs: d_dur_pred [B,L],
- * d_energy_pred [B,L] (untouched if no energy conditioning), d_dec_lens [B] int64, and d_summary (int32[2], may be
- * NULL): [0] = max(dec_lens) — the one value the caller has to read on the host before decode (the reference's own
+ * d_energy_pred [B,L] (untouched if no energy conditioning), d_dec_lens [B] int64, and d_summary (int32[2 + B], may be
+ * NULL): [2..] = dec_lens as int32 (so that ONE device -> host read gives the caller every frame count), [0] = max(dec_lens) — the one value the caller has to read on the host before decode (the reference's own
  * sync, model.py:76) — and [1] = input status bits from encode: 1 token id outside [0, n_symbols), 2 padding that is
  * not trailing or an empty utterance, 4 speaker id outside [0, n_speakers). */
 int ttsb_fastpitch_condition(ttsb_fastpitch_t* h, int B, int L, const float* d_log_dur,

@@ -247,3 +247,35 @@ def test_generator_cuda_graph_replay_matches_stream_launches(vocoder):
     out2 = replay(mel2).clone()
     assert torch.equal(out2.view(-1), vocoder(mel2).view(-1))
     assert vocoder.capture_graph(mel2) is not None and len(vocoder._graphs) == 1     # same shape: same graph
+
+
+def test_generator_runs_chunks_at_their_own_length_bit_exactly(fp_const4):
+    """Mixed-length batches (BASELINE config 5): with the frame counts on the host the generator processes the padded
+    batch in chunks that each run at their own longest utterance — same samples, no padded frames computed."""
+    from tts_arabic_pytorch_b200.vocoder.hifigan.env import AttrDict
+    from tts_arabic_pytorch_b200.vocoder.hifigan.models import Generator
+    os.environ['TTSB_HIFIGAN_CHUNK_FRAMES'] = '600'          # read at handle creation: several chunks in this test
+    try:
+        g = Generator(AttrDict(synth.HIFIGAN_CONFIG))
+        g.load_state_dict(synth.hifigan_state_dict(1235))
+        g.eval()
+        g.remove_weight_norm()
+        g = g.to(_dev())
+        gen = torch.Generator().manual_seed(3)
+        lens = [200, 150, 120, 64, 10, 1]
+        mel = torch.clamp(torch.randn(6, 80, 200, generator=gen) * 2 - 5, -11.5129, 2.0).to(_dev())
+        lt = torch.tensor(lens)
+        full = g.run(mel_f32=mel, lens=lt)
+        ragged = g.run(mel_f32=mel, lens=lt, lens_host=lens)
+        assert torch.equal(full, ragged)
+        # channel-last input straight from FastPitch (strided chunks of the caller's [B, T, 128] tensor)
+        ids = torch.zeros(5, 40, dtype=torch.long)
+        for b, n in enumerate([40, 33, 20, 7, 2]):
+            ids[b, :n] = torch.randint(1, 40, (n,), generator=gen)
+        _, dec_lens, _, _, _, mel_cl = fp_const4.infer(ids, return_channel_last=True)
+        assert dec_lens.host_list == [160, 132, 80, 28, 8]
+        a = g.run(mel_cl=mel_cl, lens=dec_lens)                       # uses dec_lens.host_list
+        b = g.run(mel_cl=mel_cl, lens=dec_lens.clone())               # no host copy: whole batch at T
+        assert torch.equal(a, b)
+    finally:
+        os.environ.pop('TTSB_HIFIGAN_CHUNK_FRAMES', None)

@@ -55,7 +55,7 @@ _SIGNATURES = {
     'ttsb_hifigan_destroy': (None, [c_void_p]),
     'ttsb_hifigan_hop': (c_int, [c_void_p]),
     'ttsb_hifigan_workspace_bytes': (c_size_t, [c_void_p, c_int, c_int]),
-    'ttsb_hifigan_forward': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+    'ttsb_hifigan_forward': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                      c_size_t, c_void_p]),
     'ttsb_fastpitch_create': (c_int, [ctypes.POINTER(FastpitchConfig), ctypes.POINTER(TensorDesc), c_int, c_int,
                                       ctypes.POINTER(c_void_p)]),

@@ -63,6 +63,7 @@ struct ConvRuntime {
     float* simt_scratch = nullptr;
     size_t simt_scratch_elems = 0;
     long long* timeline = nullptr;  // debug timeline buffer (256 CTAs x 64 slots) or null
+    int in_t_stride = 0;            // conv_tc2 only: rows between utterances of the INPUT tensor (0 = T), see get_act_tensor_map
 };
 
 // in: [B, T, ld_in] fp16 channel-last. epi.T / epi.n_total / epi.bias are filled from the layer.
@@ -71,7 +72,7 @@ int conv_forward(const ConvLayer& L, const ConvRuntime& rt, const __half* in, in
 
 // shared by the tcgen05 kernels (defined in conv_tc2.cu)
 int get_act_tensor_map(const __half* in, int ld_in, int B, int T, int cin, int chunk_k, int rows_panel,
-                       const CUtensorMap** out);
+                       const CUtensorMap** out, int t_stride = 0);
 int num_sms();
 
 // ------------------------------------------------------------------------------------------------

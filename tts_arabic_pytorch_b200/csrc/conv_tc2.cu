@@ -434,23 +434,26 @@ static PFN_encodeTiled2 get_encode_fn2() {
 // Tensor maps are pure functions of (pointer, geometry): memoise them, the same workspace buffers
 // come back every step (host time matters once a step is ~10^3 launches of ~50 us).
 int get_act_tensor_map(const __half* in, int ld_in, int B, int T, int cin, int chunk_k, int rows_panel,
-                       const CUtensorMap** out) {
+                       const CUtensorMap** out, int t_stride) {
+    // t_stride (0 = T): rows between two utterances in memory when the tensor holds more rows per utterance than the T
+    // this launch looks at (the generator runs each chunk of a padded batch at the chunk's own longest length)
+    if (t_stride <= 0) t_stride = T;
     PFN_encodeTiled2 enc = get_encode_fn2();
     TTSB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled driver entry point not available");
     TTSB_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (ld_in % 8) == 0, "input alignment");
     struct TmKey {
-        const void* p; int ld, B, T, cin, ck, rows;
+        const void* p; int ld, B, T, cin, ck, rows, ts;
         bool operator==(const TmKey& o) const {
-            return p == o.p && ld == o.ld && B == o.B && T == o.T && cin == o.cin && ck == o.ck && rows == o.rows;
+            return p == o.p && ld == o.ld && B == o.B && T == o.T && cin == o.cin && ck == o.ck && rows == o.rows && ts == o.ts;
         }
     };
     static thread_local std::vector<std::pair<TmKey, CUtensorMap>> cache;
-    const TmKey key{in, ld_in, B, T, cin, chunk_k, rows_panel};
+    const TmKey key{in, ld_in, B, T, cin, chunk_k, rows_panel, t_stride};
     for (auto& kv : cache)
         if (kv.first == key) { *out = &kv.second; return 0; }
     CUtensorMap tm_new;
     cuuint64_t dims[3] = {static_cast<cuuint64_t>(cin), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(B)};
-    cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld_in) * 2, static_cast<cuuint64_t>(T) * ld_in * 2};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld_in) * 2, static_cast<cuuint64_t>(t_stride) * ld_in * 2};
     cuuint32_t box[3] = {static_cast<cuuint32_t>(chunk_k), static_cast<cuuint32_t>(rows_panel), 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&tm_new, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(in), dims, strides, box, estr,
@@ -531,7 +534,7 @@ int conv_forward_tc2(const ConvLayer& L, const ConvRuntime& rt, const __half* in
     }
 
     const CUtensorMap* tmp = nullptr;
-    TTSB_PROPAGATE(get_act_tensor_map(in, ld_in, B, T, L.cin, L.chunk_k, L.rows_panel, &tmp));
+    TTSB_PROPAGATE(get_act_tensor_map(in, ld_in, B, T, L.cin, L.chunk_k, L.rows_panel, &tmp, rt.in_t_stride));
     const CUtensorMap tm = *tmp;      // by value: the cache may reallocate on the next lookup
 
     ConvTc2Args a;

@@ -387,8 +387,10 @@ int ttsb_fastpitch_condition(ttsb_fastpitch_t* h, int B, int L, const float* d_l
     TTSB_CHECK_CUDA(cudaMemsetAsync(st.summary, 0, sizeof(int), stream));     // [0] only: the input status of encode stays
     TTSB_PROPAGATE(launch_durations(d_log_dur, d_dur_tgt, pace, max_duration, B, L, d_dur_pred, st.cum,
                                     st.dec_lens, d_dec_lens, st.summary, stream));
-    if (d_summary)
+    if (d_summary) {
         TTSB_CHECK_CUDA(cudaMemcpyAsync(d_summary, st.summary, 2 * sizeof(int), cudaMemcpyDeviceToDevice, stream));
+        TTSB_CHECK_CUDA(cudaMemcpyAsync(d_summary + 2, st.dec_lens, B * sizeof(int), cudaMemcpyDeviceToDevice, stream));
+    }
     prof_mark(PROF_NONE, stream);
     return 0;
     });

@@ -232,7 +232,7 @@ size_t ttsb_hifigan_workspace_bytes(const ttsb_hifigan_t* h, int B, int T) {
 }
 
 int ttsb_hifigan_forward(ttsb_hifigan_t* h, const float* d_mel_f32, const void* d_mel_cl,
-                         const int32_t* d_lens, int B, int T, float* d_wav, void* d_workspace,
+                         const int32_t* d_lens, const int32_t* h_lens, int B, int T, float* d_wav, void* d_workspace,
                          size_t workspace_bytes, void* stream_) {
     return guarded_call([&]() -> int {
     TTSB_REQUIRE(h && d_wav && d_workspace, "null argument");
@@ -258,17 +258,38 @@ int ttsb_hifigan_forward(ttsb_hifigan_t* h, const float* d_mel_f32, const void* 
     static const bool act_chain = getenv("TTSB_ACT_CHAIN") ? atoi(getenv("TTSB_ACT_CHAIN")) != 0 : true;
     const float kSlope = 0.1f;   // LRELU_SLOPE (hifigan/models.py:9)
 
-    for (int b0 = 0; b0 < B; b0 += bc_max) {
-        const int bc = std::min(bc_max, B - b0);
+    // With a host copy of the lengths every chunk runs at ITS OWN longest utterance instead of the batch's: in a padded
+    // mixed-length batch (BASELINE config 5: 64..256 phonemes) 37 % of the frames are padding, and every layer of the
+    // generator would compute (and then zero) them. Chunks take as many consecutive utterances as fit the workspace.
+    const bool ragged = h_lens != nullptr && d_lens != nullptr && rt.impl == IMPL_TC && rt.tc_version == 2;
+    const long frame_budget = static_cast<long>(bc_max) * T;
+    for (int b0 = 0; b0 < B;) {
+        int bc = std::min(bc_max, B - b0);
+        const int T_full = T;
+        int Tc = T_full;
+        if (ragged) {
+            int longest = 1;
+            bc = 0;
+            while (b0 + bc < B) {
+                const int l = std::max(longest, std::min(std::max(h_lens[b0 + bc], 1), T_full));
+                if (bc > 0 && static_cast<long>(bc + 1) * l > frame_budget) break;
+                longest = l;
+                ++bc;
+            }
+            Tc = longest;
+        }
+        const int T = Tc;                     // rows per utterance of every buffer of this chunk
         const int* lens = d_lens ? d_lens + b0 : nullptr;
         const __half* mel_in;
+        rt.in_t_stride = 0;
         if (d_mel_f32) {
             prof_mark(PROF_VOC_PACK, stream);
-            TTSB_PROPAGATE(launch_pack_mel(d_mel_f32 + static_cast<size_t>(b0) * cfg.num_mels * T, lens, bc,
-                                           cfg.num_mels, T, melp, h->mel_ld, stream));
+            TTSB_PROPAGATE(launch_pack_mel(d_mel_f32 + static_cast<size_t>(b0) * cfg.num_mels * T_full, lens, bc,
+                                           cfg.num_mels, T, melp, h->mel_ld, stream, T_full));
             mel_in = melp;
         } else {
-            mel_in = static_cast<const __half*>(d_mel_cl) + static_cast<size_t>(b0) * T * h->mel_ld;
+            mel_in = static_cast<const __half*>(d_mel_cl) + static_cast<size_t>(b0) * T_full * h->mel_ld;
+            rt.in_t_stride = T_full;          // conv_pre reads the caller's [B, T_full, ld] tensor, T rows per utterance
         }
         int cur = 0;
         {
@@ -277,6 +298,7 @@ int ttsb_hifigan_forward(ttsb_hifigan_t* h, const float* d_mel_f32, const void* 
             e.out_act = NXT[cur]; e.ld_act = cfg.upsample_initial_channel; e.act_slope = 0.1f;
             prof_mark(PROF_VOC_PRE, stream);
             TTSB_PROPAGATE(conv_forward(h->conv_pre, rt, mel_in, h->mel_ld, bc, T, e, stream));
+            rt.in_t_stride = 0;
         }
         int cin = cfg.upsample_initial_channel;
         int up = 1;
@@ -356,9 +378,14 @@ int ttsb_hifigan_forward(ttsb_hifigan_t* h, const float* d_mel_f32, const void* 
             cin = C;
         }
         prof_mark(PROF_VOC_POST, stream);
-        TTSB_PROPAGATE(launch_conv_post_tanh(NXT[cur], h->post_w, h->post_b, lens, h->hop, bc, T * h->hop,
-                                             d_wav + static_cast<size_t>(b0) * T * h->hop, stream));
+        float* wav0 = d_wav + static_cast<size_t>(b0) * T_full * h->hop;
+        TTSB_PROPAGATE(launch_conv_post_tanh(NXT[cur], h->post_w, h->post_b, lens, h->hop, bc, T * h->hop, wav0, stream,
+                                             T_full * h->hop));
+        if (T < T_full)    // samples beyond the chunk's longest utterance are part of the padded output: zeros
+            TTSB_CHECK_CUDA(cudaMemset2DAsync(wav0 + static_cast<size_t>(T) * h->hop, static_cast<size_t>(T_full) * h->hop * sizeof(float),
+                                              0, static_cast<size_t>(T_full - T) * h->hop * sizeof(float), bc, stream));
         prof_mark(PROF_NONE, stream);
+        b0 += bc;
     }
     return 0;
     });

@@ -7,13 +7,15 @@ namespace ttsb {
 
 // [B,80,T] fp32 (reference mel layout, hifigan/models.py:111) -> channel-last fp16 [B,T,ld]
 // (ld >= C, channels [C,ld) zero), rows >= lens[b] zeroed (per-utterance zero padding).
+// t_stride (0 = T): frames per utterance of `mel` in memory when only the first T are packed
 int launch_pack_mel(const float* mel, const int* lens, int B, int C, int T, __half* out, int ld,
-                    cudaStream_t s);
+                    cudaStream_t s, int t_stride = 0);
 
 // conv_post (Conv1d 32->1 k7 p3) + tanh on the already leaky-relu'd stage-4 activations
 // (hifigan/models.py:123-125). x: [B,N,32] fp16, w: [7][32] fp32 (tap-major), wav: [B,N] fp32.
+// n_stride (0 = N): samples per utterance of `wav` in memory when only the first N are written
 int launch_conv_post_tanh(const __half* x, const float* w, float bias, const int* lens, int len_mul,
-                          int B, int N, float* wav, cudaStream_t s);
+                          int B, int N, float* wav, cudaStream_t s, int n_stride = 0);
 
 // word embedding gather + sinusoidal positional embedding * mask + conditioning
 // (transformer.py:212-219, 34-48). ids int64 [B,L]; out fp16 [B,L,D].

@@ -11,7 +11,7 @@ namespace ttsb {
 // pack_mel: [B,C,T] fp32 -> [B,T,ld] fp16 (transpose through smem, 32x32 tiles)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pack_mel_kernel(const float* __restrict__ mel,
-                                                       const int* __restrict__ lens, int C, int T,
+                                                       const int* __restrict__ lens, int C, int T, int t_stride,
                                                        __half* __restrict__ out, int ld) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(256) pack_mel_kernel(const float* __restrict__
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 rows per pass
     for (int r = ty; r < 32; r += 8) {
         const int c = c0 + r, t = t0 + tx;
-        tile[r][tx] = (c < C && t < T && t < len) ? mel[(static_cast<size_t>(b) * C + c) * T + t] : 0.f;
+        tile[r][tx] = (c < C && t < T && t < len) ? mel[(static_cast<size_t>(b) * C + c) * t_stride + t] : 0.f;
     }
     __syncthreads();
     for (int r = ty; r < 32; r += 8) {
@@ -30,9 +30,9 @@ __global__ void __launch_bounds__(256) pack_mel_kernel(const float* __restrict__
 }
 
 int launch_pack_mel(const float* mel, const int* lens, int B, int C, int T, __half* out, int ld,
-                    cudaStream_t s) {
+                    cudaStream_t s, int t_stride) {
     dim3 grid(ceil_div(T, 32), ceil_div(ld, 32), B);
-    pack_mel_kernel<<<grid, 256, 0, s>>>(mel, lens, C, T, out, ld);
+    pack_mel_kernel<<<grid, 256, 0, s>>>(mel, lens, C, T, t_stride > 0 ? t_stride : T, out, ld);
     count_launch();
     TTSB_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -47,7 +47,7 @@ int launch_pack_mel(const float* mel, const int* lens, int B, int C, int T, __ha
 __global__ void __launch_bounds__(256) conv_post_tanh_kernel(const __half* __restrict__ x,
                                                              const float* __restrict__ w, float bias,
                                                              const int* __restrict__ lens, int len_mul,
-                                                             int N, float* __restrict__ wav) {
+                                                             int N, int n_stride, float* __restrict__ wav) {
     constexpr int kPitch = 80;                       // bytes per staged row (64 B of data)
     __shared__ __align__(16) uint8_t sx[262 * kPitch];
     __shared__ __align__(16) float sw[7 * 32];
@@ -79,13 +79,13 @@ __global__ void __launch_bounds__(256) conv_post_tanh_kernel(const __half* __res
         }
     }
     const int len = lens ? lens[b] * len_mul : N;
-    wav[static_cast<size_t>(b) * N + n] = n < len ? tanhf(acc) : 0.f;
+    wav[static_cast<size_t>(b) * n_stride + n] = n < len ? tanhf(acc) : 0.f;
 }
 
 int launch_conv_post_tanh(const __half* x, const float* w, float bias, const int* lens, int len_mul,
-                          int B, int N, float* wav, cudaStream_t s) {
+                          int B, int N, float* wav, cudaStream_t s, int n_stride) {
     dim3 grid(ceil_div(N, 256), B);
-    conv_post_tanh_kernel<<<grid, 256, 0, s>>>(x, w, bias, lens, len_mul, N, wav);
+    conv_post_tanh_kernel<<<grid, 256, 0, s>>>(x, w, bias, lens, len_mul, N, n_stride > 0 ? n_stride : N, wav);
     count_launch();
     TTSB_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -304,8 +304,20 @@ __device__ __forceinline__ void t2_attention_body(float* sm, int b, const float*
     }
     __syncthreads();
     for (int m = threadIdx.x; m < M; m += blockDim.x) {
+        // loads of four positions are issued before their multiply-adds (same summation order, four L2 round trips in
+        // flight instead of one per position)
         float acc = 0.f;
-        for (int l = 0; l < len; ++l) acc += e[l] * memory[(static_cast<size_t>(b) * L + l) * M + m];
+        const float* mp = memory + static_cast<size_t>(b) * L * M + m;
+        int l = 0;
+        for (; l + 4 <= len; l += 4) {
+            const float v0 = mp[static_cast<size_t>(l) * M], v1 = mp[static_cast<size_t>(l + 1) * M];
+            const float v2 = mp[static_cast<size_t>(l + 2) * M], v3 = mp[static_cast<size_t>(l + 3) * M];
+            acc += e[l] * v0;
+            acc += e[l + 1] * v1;
+            acc += e[l + 2] * v2;
+            acc += e[l + 3] * v3;
+        }
+        for (; l < len; ++l) acc += e[l] * mp[static_cast<size_t>(l) * M];
         ctx[static_cast<size_t>(b) * M + m] = acc;
     }
 }
@@ -381,12 +393,15 @@ struct T2PersistArgs {
     float *ah[2], *ac, *dh[2], *dc, *aw, *awc, *ctx, *frame, *x, *gate, *frames, *align;
     int *finished, *mel_lens, *done_step;
     unsigned* bar;                   // grid barrier counter (zeroed before the launch)
+    long long* timeline;             // debug (tools/t2_phases.py): CTA 0 and CTA B-1... accumulate cycles per phase, or null
     int* err_flag;
     const __half *pre_w0, *pre_w1, *arnn_wih, *arnn_whh, *drnn_wih, *drnn_whh, *w_query, *w_proj;
     const float *arnn_b, *drnn_b, *loc_conv, *loc_dense, *att_v, *b_proj;
 };
 
-// LSTMCell for the persistent decoder: a 1024-thread CTA owns 8 hidden units (warp = 4 * unit + gate) and first stages
+// LSTMCell for the persistent decoder: a 512-thread CTA owns 8 hidden units (warp = 2 * unit + gate pair: every warp
+// computes TWO gate rows per pass over the staged vectors, which halves the shared-memory reads that bound this phase —
+// 16 warps x 86 KB instead of 32 x 86 KB per cell and step) and first stages
 // the input vectors [x1 | x2 | h] of up to 8 utterances in shared memory — every gate row of the CTA multiplies the same
 // vectors, and reading them per warp through ld.global.cg (no L1 in a persistent kernel, see ld_state4) cost ~250 MB of
 // L2 traffic per cell and step. Same per-lane accumulation order as t2_lstm_cell_body: identical results.
@@ -397,12 +412,11 @@ __device__ __forceinline__ void t2_lstm_cell_staged(float* st, float (*g_s)[4][6
                                                     const __half* __restrict__ w_hh, const float* __restrict__ bias, int H,
                                                     int B) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int u = warp >> 2, gate = warp & 3;
+    const int u = warp >> 1, g0 = (warp & 1) * 2;          // gates g0 and g0 + 1 of hidden unit u
     const int j = cta * 8 + u;
-    const int grow = gate * H + j;
     const int n_in = n1 + n2, n_tot = n_in + H;
-    const __half* wi = w_ih + static_cast<size_t>(grow) * n_in;
-    const __half* wh = w_hh + static_cast<size_t>(grow) * H;
+    const __half* wi[2] = {w_ih + static_cast<size_t>(g0 * H + j) * n_in, w_ih + static_cast<size_t>((g0 + 1) * H + j) * n_in};
+    const __half* wh[2] = {w_hh + static_cast<size_t>(g0 * H + j) * H, w_hh + static_cast<size_t>((g0 + 1) * H + j) * H};
     for (int b0 = 0; b0 < B; b0 += 8) {
         const int nb = min(8, B - b0);
         const int quads = n_tot >> 2;
@@ -414,26 +428,36 @@ __device__ __forceinline__ void t2_lstm_cell_staged(float* st, float (*g_s)[4][6
             *reinterpret_cast<float4*>(st + q * n_tot + k) = ld_state4(src);
         }
         __syncthreads();
-        float acc[8];
+        float acc[2][8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[r][q] = 0.f;
         for (int i = lane * 8; i < n_tot; i += 256) {
-            float f[8];
-            if (i < n_in) load8h(wi + i, f); else load8h(wh + (i - n_in), f);
+            float f[2][8];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                if (i < n_in) load8h(wi[r] + i, f[r]); else load8h(wh[r] + (i - n_in), f[r]);
+            }
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 if (q < nb) {
                     const float4 a = *reinterpret_cast<const float4*>(st + q * n_tot + i);
                     const float4 bb = *reinterpret_cast<const float4*>(st + q * n_tot + i + 4);
-                    acc[q] += f[0] * a.x + f[1] * a.y + f[2] * a.z + f[3] * a.w + f[4] * bb.x + f[5] * bb.y + f[6] * bb.z + f[7] * bb.w;
+#pragma unroll
+                    for (int r = 0; r < 2; ++r)
+                        acc[r][q] += f[r][0] * a.x + f[r][1] * a.y + f[r][2] * a.z + f[r][3] * a.w + f[r][4] * bb.x + f[r][5] * bb.y +
+                                     f[r][6] * bb.z + f[r][7] * bb.w;
                 }
             }
         }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const float v = warp_sum(acc[q]);
-            if (lane == 0 && q < nb) g_s[u][gate][b0 + q] = v + bias[grow];
-        }
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float v = warp_sum(acc[r][q]);
+                if (lane == 0 && q < nb) g_s[u][g0 + r][b0 + q] = v + bias[(g0 + r) * H + j];
+            }
         __syncthreads();
     }
     if (threadIdx.x < 8 * B) {
@@ -466,7 +490,7 @@ __device__ __forceinline__ void t2_grid_barrier(unsigned* bar, unsigned target, 
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(1024, 1) t2_decoder_persistent_kernel(const T2PersistArgs a) {
+__global__ void __launch_bounds__(512, 1) t2_decoder_persistent_kernel(const T2PersistArgs a) {
     extern __shared__ float sm[];
     float (*g_s)[4][64] = reinterpret_cast<float (*)[4][64]>(sm);           // [8 units][4 gates][64 utterances]
     float* st = sm + 8 * 4 * 64;                                             // staged LSTM inputs, [8][n_in + H]
@@ -478,31 +502,48 @@ __global__ void __launch_bounds__(1024, 1) t2_decoder_persistent_kernel(const T2
     for (int b = blockIdx.x; b < a.B; b += G)
         t2_prenet_body(sm, b, a.frame, a.pre_w0, a.pre_w1, a.masks, a.masks + static_cast<size_t>(a.B) * a.P, a.n_mel, a.P, a.x);
     t2_grid_barrier(a.bar, ++n_bar * G, a.err_flag);
+    // debug: cycles of CTA 0 in [A, barrier, B, barrier, C, barrier, D, barrier], summed over the chunk's steps
+    long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const bool tl = a.timeline != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    long long t_prev = tl ? clock64() : 0;
+    auto lap = [&](int k) {
+        if (tl) { const long long t = clock64(); ph[k] += t - t_prev; t_prev = t; }
+    };
     for (int i = 0; i < a.n_steps; ++i) {
         const int step = a.step0 + i;
         const int cur = step & 1, nxt = cur ^ 1;
         // A: attention LSTM cell on [prenet out | previous context]
         for (int vb = blockIdx.x; vb < lstm_blocks; vb += G)
             t2_lstm_cell_staged(st, g_s, vb, a.x, a.P, a.ctx, a.M, a.ah[cur], a.ah[nxt], a.ac, a.arnn_wih, a.arnn_whh, a.arnn_b, a.H, a.B);
+        lap(0);
         t2_grid_barrier(a.bar, ++n_bar * G, a.err_flag);
+        lap(1);
         // B: location-sensitive attention, one utterance per CTA
         for (int b = blockIdx.x; b < a.B; b += G) {
             t2_attention_body(sm, b, a.ah[nxt], a.memory, a.pmem, a.lens, a.w_query, a.loc_conv, a.loc_dense, a.att_v, a.aw, a.awc,
                               a.ctx, a.align + static_cast<size_t>(step) * a.B * a.L, a.L, a.H, a.M, a.A, a.NF, a.KL);
             __syncthreads();
         }
+        lap(2);
         t2_grid_barrier(a.bar, ++n_bar * G, a.err_flag);
+        lap(3);
         // C: decoder LSTM cell on [attention hidden | context]
         for (int vb = blockIdx.x; vb < lstm_blocks; vb += G)
             t2_lstm_cell_staged(st, g_s, vb, a.ah[nxt], a.H, a.ctx, a.M, a.dh[cur], a.dh[nxt], a.dc, a.drnn_wih, a.drnn_whh, a.drnn_b, a.H, a.B);
+        lap(4);
         t2_grid_barrier(a.bar, ++n_bar * G, a.err_flag);
+        lap(5);
         // D: mel frame + gate, stop bookkeeping, next prenet — per utterance, no grid barrier in between
         for (int b = blockIdx.x; b < a.B; b += G) {
-            const float* dhb = a.dh[nxt] + static_cast<size_t>(b) * a.H;
-            const float* cb = a.ctx + static_cast<size_t>(b) * a.M;
+            // [decoder hidden | context] of this utterance once into shared memory: 81 rows multiply it
+            float* hc = sm;
+            for (int k = threadIdx.x * 4; k < a.H + a.M; k += blockDim.x * 4)
+                *reinterpret_cast<float4*>(hc + k) = ld_state4(k < a.H ? a.dh[nxt] + static_cast<size_t>(b) * a.H + k
+                                                                       : a.ctx + static_cast<size_t>(b) * a.M + (k - a.H));
+            __syncthreads();
             for (int o = warp; o <= a.n_mel; o += nwarp) {
                 const __half* wr = a.w_proj + static_cast<size_t>(o) * (a.H + a.M);
-                const float d = warp_dot_h<true>(wr, dhb, a.H, lane) + warp_dot_h<true>(wr + a.H, cb, a.M, lane) + a.b_proj[o];
+                const float d = warp_dot_h(wr, hc, a.H, lane) + warp_dot_h(wr + a.H, hc + a.H, a.M, lane) + a.b_proj[o];
                 if (lane == 0) {
                     if (o < a.n_mel) {
                         a.frame[b * a.n_mel + o] = d;
@@ -522,7 +563,9 @@ __global__ void __launch_bounds__(1024, 1) t2_decoder_persistent_kernel(const T2
             }
             __syncthreads();
         }
+        lap(6);
         t2_grid_barrier(a.bar, ++n_bar * G, a.err_flag);
+        lap(7);
         // every CTA takes the same stop decision from the same flags
         bool all = true;
         for (int b = 0; b < a.B; ++b) all = all && (__ldcg(a.finished + b) != 0);
@@ -531,6 +574,8 @@ __global__ void __launch_bounds__(1024, 1) t2_decoder_persistent_kernel(const T2
             if (a.early_stop) break;
         }
     }
+    if (tl)
+        for (int k = 0; k < 8; ++k) a.timeline[k] += ph[k];
 }
 
 // frames [B, max_steps, n_mel] fp32 -> channel-last fp16 [B, T, ld] (zero padded channels) for the postnet
@@ -940,12 +985,14 @@ int ttsb_tacotron2_decode(ttsb_tacotron2_t* h, int B, int L, int max_steps, int 
         ConvRuntime rt;
         TTSB_PROPAGATE(get_conv_runtime(0, rt));
         a.err_flag = rt.err_flag;
+        a.timeline = rt.timeline;
         a.pre_w0 = h->pre_w0; a.pre_w1 = h->pre_w1; a.arnn_wih = h->arnn_wih; a.arnn_whh = h->arnn_whh;
         a.drnn_wih = h->drnn_wih; a.drnn_whh = h->drnn_whh; a.w_query = h->w_query; a.w_proj = h->w_proj;
         a.arnn_b = h->arnn_b; a.drnn_b = h->drnn_b; a.loc_conv = h->loc_conv; a.loc_dense = h->loc_dense; a.att_v = h->att_v;
         a.b_proj = h->b_proj;
         const size_t lstm_smem = (8 * 4 * 64 + static_cast<size_t>(8) * (std::max(P, H) + M + H)) * sizeof(float);
-        const size_t smem = std::max({att_smem, static_cast<size_t>(h->n_mel + P) * sizeof(float), lstm_smem});
+        const size_t smem = std::max({att_smem, static_cast<size_t>(h->n_mel + P) * sizeof(float), lstm_smem,
+                                      static_cast<size_t>(H + M) * sizeof(float)});
         static PerDeviceOnce configured;
         if (!configured.here()) {
             TTSB_CHECK_CUDA(cudaFuncSetAttribute(t2_decoder_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -953,13 +1000,13 @@ int ttsb_tacotron2_decode(ttsb_tacotron2_t* h, int B, int L, int max_steps, int 
         }
         TTSB_REQUIRE(smem <= 200 * 1024 && H % 8 == 0, "persistent decoder: shared-memory plan");
         int per_sm = 0;
-        TTSB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, t2_decoder_persistent_kernel, 1024, smem));
+        TTSB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, t2_decoder_persistent_kernel, 512, smem));
         TTSB_REQUIRE(per_sm >= 1, "persistent decoder does not fit on an SM");
         // one CTA per SM; one pass over the LSTM's H/8 eight-unit blocks when the device has that many SMs
         const int grid = std::min(num_sms(), std::max(H / 8, B));
         TTSB_CHECK_CUDA(cudaMemsetAsync(st.bar, 0, 4 * sizeof(unsigned), s));
         void* kargs[] = {&a};
-        TTSB_CHECK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(t2_decoder_persistent_kernel), dim3(grid), dim3(1024),
+        TTSB_CHECK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(t2_decoder_persistent_kernel), dim3(grid), dim3(512),
                                                     kargs, smem, s));
         count_launch();
         if (h_done_step) {

@@ -242,14 +242,18 @@ class FastPitch(nn.Module):
             dur_pred = torch.empty(B, L, **f32)
             energy_pred = torch.empty(B, L, **f32) if (self.energy_conditioning and e_tgt is None) else None
             dec_lens = torch.empty(B, dtype=torch.int64, device=device)
-            summary = torch.empty(2, dtype=torch.int32, device=device)
+            summary = torch.empty(2 + B, dtype=torch.int32, device=device)
             _lib.check(lib.ttsb_fastpitch_condition(handle, B, L, _lib.ptr(log_dur), _lib.ptr(pitch_in), _lib.ptr(e_tgt),
                                                     _lib.ptr(d_tgt), float(pace), float(max_duration),
                                                     _lib.ptr(dur_pred), _lib.ptr(energy_pred), _lib.ptr(dec_lens),
                                                     _lib.ptr(summary), _lib.ptr(state), _lib.ptr(ws), ws.numel(), stream))
             # THE host sync of the call — the reference's own (model.py:76: max(dec_lens) sizes the decoder batch). The
             # input checks ride on it: ids were validated on the device by encode (no extra reductions or syncs)
-            T, status = summary.tolist()
+            summ = summary.tolist()
+            T, status = summ[0], summ[1]
+            # every utterance's frame count came with the same read: the vocoder uses it to run each chunk of the padded
+            # batch at the chunk's own longest utterance (Generator.run)
+            dec_lens.host_list = summ[2:]
             if status & 1:
                 raise IndexError('token id out of range [0, %d)' % self.cfg['n_symbols'])
             if status & 4:

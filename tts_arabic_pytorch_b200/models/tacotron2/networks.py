@@ -199,7 +199,7 @@ class Tacotron2Wave(nn.Module):
         batch = torch.zeros(len(mel_list), mel_list[0].shape[0], t_max, dtype=torch.float32, device=self.device)
         for i, m in enumerate(mel_list):
             batch[i, :, :m.shape[1]] = m
-        wav = self.vocoder.run(mel_f32=batch, lens=lens)
+        wav = self.vocoder.run(mel_f32=batch, lens=lens, lens_host=lens.tolist())
         if denoise > 0:
             wav = self.denoiser.denoise_batch(wav, lens.to(wav.device) * self.vocoder.hop, denoise)
         wav = wav.cpu()

@@ -143,8 +143,10 @@ class Generator(nn.Module):
     def _device(self):
         return self.conv_post.bias.device
 
-    def run(self, mel_f32=None, mel_cl=None, lens=None):
-        """Padded batch -> [B, T*hop] fp32. `mel_f32` [B,80,T] or `mel_cl` [B,T,128] fp16."""
+    def run(self, mel_f32=None, mel_cl=None, lens=None, lens_host=None):
+        """Padded batch -> [B, T*hop] fp32. `mel_f32` [B,80,T] or `mel_cl` [B,T,128] fp16. lens_host: the frame counts as a
+        Python list when the caller already has them on the host (FastPitch.infer attaches them to the `dec_lens` it
+        returns): the padded batch then runs in chunks at each chunk's own longest utterance (ttsb_hifigan_forward)."""
         device = self._device()
         if device.type != 'cuda':
             raise RuntimeError('tts_arabic_pytorch_b200 has no CPU path: move the vocoder to a CUDA device '
@@ -158,13 +160,18 @@ class Generator(nn.Module):
             assert mel_cl.dtype == torch.float16 and mel_cl.is_contiguous() and mel_cl.device == device
             B, T, _ = mel_cl.shape
         if lens is not None:
+            if lens_host is None:
+                lens_host = getattr(lens, 'host_list', None)
             lens = lens.to(device=device, dtype=torch.int32).contiguous()
+        h_lens = None
+        if lens is not None and lens_host is not None and len(lens_host) == B:
+            h_lens = (ctypes.c_int32 * B)(*[int(x) for x in lens_host])
         with torch.cuda.device(device):
             handle = self._get_handle(device)
             wav = torch.empty(B, T * self.hop, dtype=torch.float32, device=device)
             nbytes = lib.ttsb_hifigan_workspace_bytes(handle, B, T)
             ws = self._ws.get(nbytes, device)
-            _lib.check(lib.ttsb_hifigan_forward(handle, _lib.ptr(mel_f32), _lib.ptr(mel_cl), _lib.ptr(lens), B, T,
+            _lib.check(lib.ttsb_hifigan_forward(handle, _lib.ptr(mel_f32), _lib.ptr(mel_cl), _lib.ptr(lens), h_lens, B, T,
                                                 _lib.ptr(wav), _lib.ptr(ws), nbytes, _lib.current_stream(device)))
         del src
         return wav
