@@ -22,7 +22,7 @@ def main():
     import warnings
     warnings.simplefilter('ignore')
     m.infer(tok)
-    tl = torch.zeros(256 * 128, dtype=torch.int64, device='cuda')
+    tl = torch.zeros(257 * 128, dtype=torch.int64, device='cuda')
     lib.ttsb_debug_set_timeline(_lib.ptr(tl))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -30,7 +30,7 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     lib.ttsb_debug_set_timeline(None)
-    v = tl[:8].tolist()
+    v = tl[256 * 128:256 * 128 + 8].tolist()
     names = ['A attention LSTM', 'barrier', 'B attention', 'barrier', 'C decoder LSTM', 'barrier', 'D proj+prenet', 'barrier']
     tot = sum(v)
     print('persistent decoder, B=%d, %d steps: %.1f us per step (whole infer: %.2f ms)' % (B, steps, e0.elapsed_time(e1) * 1e3 / steps, e0.elapsed_time(e1)))

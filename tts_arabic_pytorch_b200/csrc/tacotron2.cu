@@ -39,13 +39,28 @@ __device__ __forceinline__ float4 ld_state4(const float* p) { return __ldcg(rein
 // dot(w_row[0:n] (fp16), x[0:n] (fp32)) by one warp; n % 8 == 0. kState: x is such a state vector in global memory.
 template <bool kState = false>
 __device__ __forceinline__ float warp_dot_h(const __half* __restrict__ w, const float* __restrict__ x, int n, int lane) {
+    // Four weight loads are issued before the first multiply-add of a pass: the weights come from L2 (~700 cycles), and a
+    // one-load-per-iteration loop made every row cost (iterations x L2 latency) — the decoder's per-step time was that
+    // latency chain, not bandwidth or arithmetic (tools/t2_phases.py, round 2). Same per-lane summation order.
     float acc = 0.f;
-    for (int i = lane * 8; i < n; i += 256) {
-        float f[8];
-        load8h(w + i, f);
-        const float4 a = kState ? ld_state4(x + i) : *reinterpret_cast<const float4*>(x + i);
-        const float4 b = kState ? ld_state4(x + i + 4) : *reinterpret_cast<const float4*>(x + i + 4);
-        acc += f[0] * a.x + f[1] * a.y + f[2] * a.z + f[3] * a.w + f[4] * b.x + f[5] * b.y + f[6] * b.z + f[7] * b.w;
+    for (int i0 = lane * 8; i0 < n; i0 += 4 * 256) {
+        uint4 wv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = i0 + j * 256;
+            wv[j] = i < n ? __ldg(reinterpret_cast<const uint4*>(w + i)) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = i0 + j * 256;
+            if (i < n) {
+                float f[8];
+                unpack8(wv[j], f);
+                const float4 a = kState ? ld_state4(x + i) : *reinterpret_cast<const float4*>(x + i);
+                const float4 b = kState ? ld_state4(x + i + 4) : *reinterpret_cast<const float4*>(x + i + 4);
+                acc += f[0] * a.x + f[1] * a.y + f[2] * a.z + f[3] * a.w + f[4] * b.x + f[5] * b.y + f[6] * b.z + f[7] * b.w;
+            }
+        }
     }
     return warp_sum(acc);
 }
@@ -243,8 +258,13 @@ __device__ __forceinline__ void t2_attention_body(float* sm, int b, const float*
     const int len = lens[b];
     const int pad = (KL - 1) / 2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    // the query rows all multiply the same attention-LSTM output: stage it once (it was written by other CTAs: ld.cg)
+    float* ahs = sm + ((A + 2 * (L + KL) + L + 32 + 3) & ~3);   // [H], 16-byte aligned for the float4 accesses
+    for (int k = threadIdx.x * 4; k < H; k += blockDim.x * 4)
+        *reinterpret_cast<float4*>(ahs + k) = ld_state4(ah + static_cast<size_t>(b) * H + k);
+    __syncthreads();
     for (int a = warp; a < A; a += nwarp) {
-        const float d = warp_dot_h<true>(wq + static_cast<size_t>(a) * H, ah + static_cast<size_t>(b) * H, H, lane);
+        const float d = warp_dot_h(wq + static_cast<size_t>(a) * H, ahs, H, lane);
         if (lane == 0) q[a] = d;
     }
     for (int i = threadIdx.x; i < L + KL - 1; i += blockDim.x) {
@@ -260,8 +280,9 @@ __device__ __forceinline__ void t2_attention_body(float* sm, int b, const float*
             // location features f[nf] = sum_k conv[nf,0,k]*prev[l+k-pad] + conv[nf,1,k]*cum[l+k-pad]; lane = filter
             float f = 0.f;
             if (lane < NF) {
-                const float* wc = wloc_conv + static_cast<size_t>(lane) * 2 * KL;
-                for (int k = 0; k < KL; ++k) f += wc[k] * w_prev[l + k] + wc[KL + k] * w_cum[l + k];
+                // wloc_conv is stored TRANSPOSED ([2][KL][NF]): the lanes (filters) of a warp read one line per tap
+                for (int k = 0; k < KL; ++k)
+                    f += wloc_conv[k * NF + lane] * w_prev[l + k] + wloc_conv[(KL + k) * NF + lane] * w_cum[l + k];
             }
             for (int a = lane; a < A; a += 32) {
                 float s = q[a] + pmem[(static_cast<size_t>(b) * L + l) * A + a];
@@ -433,21 +454,35 @@ __device__ __forceinline__ void t2_lstm_cell_staged(float* st, float (*g_s)[4][6
         for (int r = 0; r < 2; ++r)
 #pragma unroll
             for (int q = 0; q < 8; ++q) acc[r][q] = 0.f;
-        for (int i = lane * 8; i < n_tot; i += 256) {
-            float f[2][8];
+        for (int i0 = lane * 8; i0 < n_tot; i0 += 2 * 256) {
+            // four weight loads (two rows x two column blocks) in flight per pass: see warp_dot_h
+            uint4 wv[2][2];
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                if (i < n_in) load8h(wi[r] + i, f[r]); else load8h(wh[r] + (i - n_in), f[r]);
+            for (int jj = 0; jj < 2; ++jj) {
+                const int i = i0 + jj * 256;
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+                    wv[jj][r] = i < n_tot ? __ldg(reinterpret_cast<const uint4*>(i < n_in ? wi[r] + i : wh[r] + (i - n_in)))
+                                          : make_uint4(0, 0, 0, 0);
             }
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                if (q < nb) {
-                    const float4 a = *reinterpret_cast<const float4*>(st + q * n_tot + i);
-                    const float4 bb = *reinterpret_cast<const float4*>(st + q * n_tot + i + 4);
+            for (int jj = 0; jj < 2; ++jj) {
+                const int i = i0 + jj * 256;
+                if (i < n_tot) {
+                    float f[2][8];
+                    unpack8(wv[jj][0], f[0]);
+                    unpack8(wv[jj][1], f[1]);
 #pragma unroll
-                    for (int r = 0; r < 2; ++r)
-                        acc[r][q] += f[r][0] * a.x + f[r][1] * a.y + f[r][2] * a.z + f[r][3] * a.w + f[r][4] * bb.x + f[r][5] * bb.y +
-                                     f[r][6] * bb.z + f[r][7] * bb.w;
+                    for (int q = 0; q < 8; ++q) {
+                        if (q < nb) {
+                            const float4 a = *reinterpret_cast<const float4*>(st + q * n_tot + i);
+                            const float4 bb = *reinterpret_cast<const float4*>(st + q * n_tot + i + 4);
+#pragma unroll
+                            for (int r = 0; r < 2; ++r)
+                                acc[r][q] += f[r][0] * a.x + f[r][1] * a.y + f[r][2] * a.z + f[r][3] * a.w + f[r][4] * bb.x +
+                                             f[r][5] * bb.y + f[r][6] * bb.z + f[r][7] * bb.w;
+                        }
+                    }
                 }
             }
         }
@@ -575,7 +610,7 @@ __global__ void __launch_bounds__(512, 1) t2_decoder_persistent_kernel(const T2P
         }
     }
     if (tl)
-        for (int k = 0; k < 8; ++k) a.timeline[k] += ph[k];
+        for (int k = 0; k < 8; ++k) a.timeline[256 * 128 + k] += ph[k];     // past the slots the conv kernels stamp
 }
 
 // frames [B, max_steps, n_mel] fp32 -> channel-last fp16 [B, T, ld] (zero padded channels) for the postnet
@@ -823,7 +858,12 @@ int ttsb_tacotron2_create(const ttsb_tensor_t* weights, int n_weights, int devic
         TTSB_PROPAGATE(upload_f32(vv->h_data, h->A, &h->att_v));
         TTSB_GET_TENSOR(lc, tab, A + "location_layer.location_conv.weight", 3);
         TTSB_REQUIRE(lc->shape[0] == h->NF && lc->shape[1] == 2 && lc->shape[2] == h->KL, "location conv shape");
-        TTSB_PROPAGATE(upload_f32(lc->h_data, TensorTable::numel(lc), &h->loc_conv));
+        std::vector<float> lct(TensorTable::numel(lc));                     // [NF][2][KL] -> [2][KL][NF] (t2_attention_body)
+        for (int nf = 0; nf < h->NF; ++nf)
+            for (int c2 = 0; c2 < 2; ++c2)
+                for (int k = 0; k < h->KL; ++k)
+                    lct[(static_cast<size_t>(c2) * h->KL + k) * h->NF + nf] = lc->h_data[(static_cast<size_t>(nf) * 2 + c2) * h->KL + k];
+        TTSB_PROPAGATE(upload_f32(lct.data(), lct.size(), &h->loc_conv));
         TTSB_GET_TENSOR(ld, tab, A + "location_layer.location_dense.weight", 2);
         TTSB_REQUIRE(ld->shape[0] == h->A && ld->shape[1] == h->NF, "location dense shape");
         std::vector<float> ldt(static_cast<size_t>(h->A) * h->NF);          // [A][NF] -> [NF][A] (t2_attention_body)
@@ -970,7 +1010,7 @@ int ttsb_tacotron2_decode(ttsb_tacotron2_t* h, int B, int L, int max_steps, int 
     cudaStream_t s = static_cast<cudaStream_t>(stream_);
     T2State st = carve_t2(h, d_state, B, L, max_steps, nullptr);
     const int H = h->H, M = h->M, P = h->P;
-    const size_t att_smem = (h->A + 2 * (L + h->KL) + L + 32) * sizeof(float);
+    const size_t att_smem = (h->A + 2 * (L + h->KL) + L + 32 + 4 + h->H) * sizeof(float);
     static const int want_persistent = getenv("TTSB_T2_PERSISTENT") ? atoi(getenv("TTSB_T2_PERSISTENT")) : 1;
     if (want_persistent) {
         // one cooperative launch for the whole chunk (t2_decoder_persistent_kernel)
