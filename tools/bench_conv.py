@@ -20,6 +20,8 @@ LAYERS = [
     ('s0_256_k11_d5', 0, 256, 256, 11, 5, 1, 8, True),
     ('ups1_256x128_s8', 1, 256, 128, 16, 1, 8, 8, False),
     ('s1_128_k3_d1', 0, 128, 128, 3, 1, 1, 64, True),
+    ('s1_128_k3_nores', 0, 128, 128, 3, 1, 1, 64, False),
+    ('s1_128_k7_nores', 0, 128, 128, 7, 3, 1, 64, False),
     ('s1_128_k7_d3', 0, 128, 128, 7, 3, 1, 64, True),
     ('s1_128_k11_d5', 0, 128, 128, 11, 5, 1, 64, True),
     ('ups2_128x64_s2', 1, 128, 64, 4, 1, 2, 64, False),

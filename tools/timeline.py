@@ -56,7 +56,7 @@ def main():
                 print('    tile %d  mma %6d %6d %6d | epi %6d %6d %6d %6d | panel %6d' % (i, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]))
                 d = [int(row[64 + i * 8 + k]) - base if int(row[64 + i * 8 + k]) > 0 else -1 for k in range(7)]
                 w = int(row[64 + i * 8 + 7])
-                print('            epi detail (lean: seen, chunk 0 res_rows / acc_loaded / math / stored, end): %s | issuer waited %d cycles in %d of the weight stages'
+                print('            epi detail (lean: seen | chunk 1: start, rows + acc loaded, math, tile released, stored | end): %s | issuer waited %d cycles in %d of the weight stages'
                       % (' '.join('%d' % a for a in d), w // 1000, w % 1000))
 
 

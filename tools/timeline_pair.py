@@ -52,8 +52,8 @@ def main():
         for i in range(7):
             v = [int(row[8 + i * 16 + j]) - base if int(row[8 + i * 16 + j]) > 0 else -1 for j in range(16)]
             print('  item %d  ' % i + ' '.join('%8d' % a for a in v))
-        d = [int(row[120 + j]) - base if int(row[120 + j]) > 0 else -1 for j in range(6)]
-        print('  final epilogue of item 4: acc seen %d, chunk 0: residual rows %d, acc loaded %d, math %d, stored %d; end %d' % tuple(d))
+        d = [int(row[120 + j]) - base if int(row[120 + j]) > 0 else -1 for j in range(7)]
+        print('  final epilogue of item 4: acc seen %d | steady chunk: start %d, rows + acc loaded %d, math %d, tile released %d, stored %d | end %d' % tuple(d))
 
 
 if __name__ == '__main__':

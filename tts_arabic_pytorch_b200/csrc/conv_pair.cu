@@ -44,6 +44,7 @@ struct ConvPairArgs {
     int tt_rows;      // TT panel rows per chunk (multiple of 8, >= 128 + 2*h2)
     int x_slots, tt_slots;
     int w2_resident, b_stages;
+    int w2_x2;        // streamed W2 only: one pass of the W2 ring feeds conv2 of TWO consecutive items (both TT slots, both acc2 buffers)
     int smem_res;     // 1: kernel instantiated with kSmemRes (host-side record; see conv_pair_forward)
     int in_act;       // 1: x is stored activated (lrelu(x)): the TMA panel IS conv1's operand — no in-place transform, the conv1
                       // issuer waits for the panel itself; the final epilogue recovers x for the residual (EpiParams::res_inv)
@@ -206,7 +207,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         if (!args.w2_resident && elect_one()) {
             int sb = 0;
             uint32_t pb = 1;
-            for (int idx = blockIdx.x; idx < args.n_work; idx += grid) {
+            // w2_x2: one pass per PAIR of items (the conv2 issuer applies every tile to both)
+            const int pass_stride = args.w2_x2 ? 2 * grid : grid;
+            for (int idx = blockIdx.x; idx < args.n_work; idx += pass_stride) {
                 const uint8_t* wp = reinterpret_cast<const uint8_t*>(args.w2);
                 for (int i = 0; i < n_btiles; ++i) {
                     mbar_wait(&empty_b[sb], pb, args.err_flag, 302);
@@ -274,6 +277,51 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 const uint32_t ttp_u = ttp_bytes >> 4, ttslot_u = ttslot_bytes >> 4;
                 int st = 0, sb = 0, b2 = 0, it = 0;
                 uint32_t ptt = 0, pb = 0, pe2 = 3;
+                // Streamed W2, two items per pass. The ring (b_stages x one per-tap tile) delivers a tile every ~560 cycles
+                // whatever the consumer does (bytes in flight / copy latency: C = 64, k = 11 timelines), against 4 x 48 cycles of
+                // MMAs per tile and item — conv2 was waiting for weights two thirds of the time. Items i and i + 1 sit in the two
+                // TT slots and accumulate into the two acc2 buffers, so every tile that arrives is applied to both: half the
+                // weight bytes per output row. (Costs latency only: conv2(i) starts once mid(i + 1) is done.)
+                if (args.w2_x2) {
+                    const uint32_t d0 = tmem_base + acc2_col, d1 = d0 + C;
+                    for (int idx = blockIdx.x; idx < args.n_work; idx += 2 * grid, it += 2) {
+                        const bool two = idx + grid < args.n_work;
+                        mbar_wait(&tt_full[0], ptt & 1u, args.err_flag, 306);
+                        mbar_wait(&acc2_empty[0], pe2 & 1u, args.err_flag, 307);
+                        if (two) {
+                            mbar_wait(&tt_full[1], (ptt >> 1) & 1u, args.err_flag, 306);
+                            mbar_wait(&acc2_empty[1], (pe2 >> 1) & 1u, args.err_flag, 307);
+                        }
+                        pe2 ^= two ? 3u : 1u;
+                        tc_fence_after();
+                        tlp_mark(args, it, 5);
+                        uint32_t accumulate = 0;
+                        for (int c = 0; c < args.n_chunks; ++c) {
+                            uint32_t a0 = tt_lo0 + c * ttp_u, a1 = a0 + ttslot_u;
+                            for (int tap = 0; tap < args.n_taps; ++tap) {
+                                mbar_wait(&full_b[sb], pb, args.err_flag, 308);
+                                tc_fence_after();
+                                const uint32_t b_lo = w2_lo0 + sb * btile_u;
+                                issue(d0, a0, b_lo, accumulate);
+                                if (two) issue(d1, a1, b_lo, accumulate);
+                                accumulate = 1;
+                                a0 += row_u;
+                                a1 += row_u;
+                                umma_commit(&empty_b[sb]);
+                                if (++sb == args.b_stages) { sb = 0; pb ^= 1; }
+                            }
+                        }
+                        umma_commit(&tt_empty[0]);
+                        umma_commit(&acc2_full[0]);
+                        if (two) {
+                            umma_commit(&tt_empty[1]);
+                            umma_commit(&acc2_full[1]);
+                        }
+                        tlp_mark(args, it, 6);
+                        if (two) tlp_mark(args, it + 1, 6);
+                        ptt ^= two ? 3u : 1u;
+                    }
+                } else
                 for (int idx = blockIdx.x; idx < args.n_work; idx += grid, ++it) {
                     mbar_wait(&tt_full[st], (ptt >> st) & 1u, args.err_flag, 306);
                     mbar_wait(&acc2_empty[b2], (pe2 >> b2) & 1u, args.err_flag, 307);
@@ -591,6 +639,8 @@ int conv_pair_forward(const ConvLayer& L1, const ConvLayer& L2, const ConvPairPl
     a.rows_panel = plan.rows_panel; a.tt_rows = plan.tt_rows;
     a.x_slots = plan.x_slots; a.tt_slots = plan.tt_slots;
     a.w2_resident = plan.w2_resident; a.b_stages = plan.b_stages;
+    static const int want_w2_x2 = getenv("TTSB_PAIR_W2X2") ? atoi(getenv("TTSB_PAIR_W2X2")) : 1;
+    a.w2_x2 = (want_w2_x2 && !plan.w2_resident && plan.tt_slots == 2) ? 1 : 0;
     a.in_act = in_act ? 1 : 0;
     a.w1 = L1.w_packed; a.w2 = L2.w_packed;
     a.bias1 = L1.bias;

@@ -60,7 +60,8 @@ __device__ __forceinline__ void tl2_mark(const ConvTc2Args& a, int slot) {
     if (blockIdx.x < 256 && slot < 64) a.timeline[blockIdx.x * 128 + slot] = clock64();
 }
 
-// kEpi: 0 = general epilogue, 1 = lean (vocoder hot subset), 2 = lean + MRF accumulate
+// kEpi: 0 = general epilogue, 1 = lean (vocoder hot subset), 2 = lean + MRF accumulate, 3 / 4 = act-only lean without / with a
+// residual (run_epilogue_act: the activated chain's single-output launches)
 template <int kTmemCols, int kMinBlocks, int kEpi>
 __global__ void __launch_bounds__(192, kMinBlocks)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ ConvTc2Args args,
@@ -339,14 +340,20 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         // item's accumulator is waited for, so its latency hides behind a whole tile
         constexpr bool kLean = kEpi != 0;
         constexpr bool kMrf = kEpi == 2;
+        constexpr bool kAct = kEpi == 3 || kEpi == 4;
         LeanPrefetch<kMrf> pre_cur, pre_nxt;
+        // kEpi == 3: nothing but lens[b] travels a tile ahead
+        auto prefetch = [&](const RowIO& io, long row0, bool on, LeanPrefetch<kMrf>& p, int pb) {
+            if (kEpi == 3) p.len_rows = (on && args.epi.lens != nullptr) ? __ldg(args.epi.lens + pb) * args.epi.len_mul : 0x7fffffff;
+            else lean_prefetch(args.epi, io, row0, n_base, on, p, pb);
+        };
         if (kLean && first < n_groups) {
             const int idx0 = first * csize + crank;
             const bool v0 = idx0 < args.n_work;
             const int b0 = v0 ? idx0 / args.groups_t : 0;
             const int w0 = (v0 ? (idx0 - b0 * args.groups_t) * args.rpp : args.groups_t * args.rpp) * kTileM + q * 32;
             RowIO io{stage, lane, min(32, max(0, args.T - w0))};
-            lean_prefetch(args.epi, io, static_cast<long>(b0) * args.T + w0, n_base, v0, pre_cur, b0);
+            prefetch(io, static_cast<long>(b0) * args.T + w0, v0, pre_cur, b0);
         }
         for (int p = first; p < n_groups; p += stride, ++tl_i) {
             const int idx = p * csize + crank;
@@ -383,9 +390,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     const int nw0 = ((nvalid ? (nidx - nb * args.groups_t) * args.rpp : args.groups_t * args.rpp) +
                                      (last_r ? 0 : r + 1)) * kTileM + q * 32;
                     RowIO nio{stage, lane, min(32, max(0, args.T - nw0))};
-                    lean_prefetch(args.epi, nio, static_cast<long>(nb) * args.T + nw0, n_base, nvalid, pre_nxt, nb);
+                    prefetch(nio, static_cast<long>(nb) * args.T + nw0, nvalid, pre_nxt, nb);
                     long long* dbg = (tl_on && args.timeline != nullptr && blockIdx.x < 256 && tl_i < 7)
                                          ? args.timeline + blockIdx.x * 128 + 64 + tl_i * 8 : nullptr;
+                    if constexpr (kAct)
+                        run_epilogue_act<kEpi == 4, kEpi == 3>(args.epi, acc.taddr, b, t, n_base, args.n_tile, wait_acc, drained, stage, stage_in,
+                                                               pre_cur, smem_u32(sbias), &tmap_act, dbg);
+                    else
                     run_epilogue_lean<kMrf, true, !(kMrf && kMinBlocks >= 2)>(args.epi, acc, b, t, n_base, args.n_tile, wait_acc, drained, stage, pre_cur,
                                             0x7fffffff, smem_u32(sbias), (args.tma_out & 1) ? &tmap_raw : nullptr,
                                             (args.tma_out & 2) ? &tmap_act : nullptr, (args.tma_out & 4) ? &tmap_mrf : nullptr, stage_in, dbg);
@@ -518,6 +529,12 @@ static bool host_epi_is_lean(const EpiParams& e) {
 template <int kCols, int kMinBlocks>
 static int launch_two(const CUtensorMap& tm, const ConvTc2Args& a, int grid, size_t smem, cudaStream_t s, const OutMaps& om) {
     if (!host_epi_is_lean(a.epi)) return launch_two_impl<kCols, kMinBlocks, 0>(tm, a, grid, smem, s, om);
+    static const int want_act = getenv("TTSB_EPI_ACT") ? atoi(getenv("TTSB_EPI_ACT")) : 1;
+    if (want_act && a.epi.mrf_mode == MRF_NONE && a.epi.out_raw == nullptr && a.epi.out_act != nullptr && (a.tma_out & 2) &&
+        a.n_tile % 64 == 0) {
+        if (a.epi.residual == nullptr) return launch_two_impl<kCols, kMinBlocks, 3>(tm, a, grid, smem, s, om);
+        if (want_act >= 2) return launch_two_impl<kCols, kMinBlocks, 4>(tm, a, grid, smem, s, om);
+    }
     if (a.epi.mrf_mode == MRF_NONE) return launch_two_impl<kCols, kMinBlocks, 1>(tm, a, grid, smem, s, om);
     return launch_two_impl<kCols, kMinBlocks, 2>(tm, a, grid, smem, s, om);
 }
@@ -561,6 +578,8 @@ int conv_forward_tc2(const ConvLayer& L, const ConvRuntime& rt, const __half* in
     }
     a.w = L.w_packed; a.err_flag = rt.err_flag; a.epi = epi;
     a.timeline = rt.timeline;
+    static const int epi_debug = getenv("TTSB_EPI_DEBUG") ? atoi(getenv("TTSB_EPI_DEBUG")) : 0;
+    a.epi.debug = epi_debug;
     static const int issue_mode = getenv("TTSB_ISSUE") ? atoi(getenv("TTSB_ISSUE")) : 2;
     a.issue_mode = issue_mode;
 

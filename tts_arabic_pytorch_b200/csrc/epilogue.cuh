@@ -52,6 +52,8 @@ struct EpiParams {
     float* out_f32_t = nullptr;     // [B, n_store, T] fp32, transposed store
     int n_store = 0;
     int f32_unmasked = 0;           // out_f32_t receives the value before row masking
+    int debug = 0;                  // timing decomposition (TTSB_EPI_DEBUG; results are WRONG when set): 1 no wait for the
+                                    // staging tile's previous TMA store, 2 no TMA store, 4 no proxy fence, 8 no epilogue math
 };
 
 #ifdef __CUDACC__
@@ -112,10 +114,19 @@ __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
     return v;
 }
 
+// timing-decomposition switches (EpiParams::debug) are compiled in only with -DTTSB_EPI_DEBUG: the epilogues sit at their
+// register budgets and even a dead runtime branch pushes them into spilling
+#ifdef TTSB_EPI_DEBUG
+constexpr bool kEpiDebug = true;
+#else
+constexpr bool kEpiDebug = false;
+#endif
+
 struct RowIO {
     uint8_t* tile;      // this warp's 2 KB staging tile, or null -> direct per-row access
     int lane;
     int rows_valid;     // rows of this warp inside [0, T): clamp(T - warp_row0, 0, 32)
+    int dbg = 0;        // EpiParams::debug
 
     // A TMA store may still be reading the tile: the lane that issued it (elect.sync = lowest lane) waits for the
     // read to finish before anyone overwrites the tile. Cheap when nothing is pending.
@@ -126,14 +137,16 @@ struct RowIO {
     // write this lane's own row (4 units) of a [32 x 32] block through ONE TMA store: the tile's XOR pattern is the
     // 64-byte TMA swizzle, so the row-owner layout goes out as it is — no LDS / STG / address arithmetic per lane.
     // (c_col, c_row, c_b) = tensor coordinates of the block; rows beyond the tensor are clipped by the TMA unit.
-    __device__ __forceinline__ void store_tma(const CUtensorMap* tm, int c_col, int c_row, int c_b, const Chunk32& own) const {
+    __device__ __forceinline__ void store_tma(const CUtensorMap* tm, int c_col, int c_row, int c_b, const Chunk32& own,
+                                              long long* dbg_released = nullptr) const {
         const uint32_t base = smem_u32(tile);
-        release_tile();
+        if (!(kEpiDebug && (dbg & 1))) release_tile();
+        if (dbg_released) *dbg_released = clock64();
 #pragma unroll
         for (int u = 0; u < 4; ++u) sts128(base + wtile_off(lane, u), own.q[u]);
-        fence_proxy_async();
+        if (!(kEpiDebug && (dbg & 4))) fence_proxy_async();
         __syncwarp();
-        if (rows_valid > 0 && elect_one()) {
+        if (rows_valid > 0 && !(kEpiDebug && (dbg & 2)) && elect_one()) {
             tma_store_3d(tm, tile, c_col, c_row, c_b);
             tma_store_commit();
         }
@@ -425,8 +438,9 @@ __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc&
     // UMMA K-major swizzled layout). res_saddr = shared address of this lane's row, res_phase = its 16-byte-unit XOR
     // pattern; 16-byte unit u of the row sits at res_saddr + ((u ^ res_phase) << 4). No global loads, no transposes and
     // none of the 32 prefetch registers of the global path.
-    // dbg (timeline tools): clock64() after 0 accumulator seen, then for the FIRST chunk 1 residual rows in registers,
-    // 2 accumulator chunk loaded, 3 math + pack done, 4 stores issued; 5 after the last chunk
+    // dbg (timeline tools): clock64() after 0 accumulator seen, then for a steady-state chunk (the second one, or the only
+    // one) 1 chunk starts, 2 residual rows in registers and accumulator chunk loaded, 3 math + pack done, 4 staging tile released by the
+    // previous TMA store (TMA outputs only), 5 stores issued; 6 after the last chunk
     // stage_in: a second 2 KB tile of this warp for the residual / MRF row transposes. With ONE tile every transpose has
     // to wait until the TMA store issued just before it (the previous chunk's output) has finished reading the tile —
     // a full TMA read latency per chunk on the epilogue's critical path (round-2 timeline: ~2000 cycles per chunk).
@@ -438,8 +452,8 @@ __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc&
     const int warp_row0 = t - lane;
     const long row0 = static_cast<long>(b) * e.T + warp_row0;
     const bool in_len = t < pre.len_rows;
-    RowIO io{stage, lane, min(32, max(0, min(e.T, t_end) - warp_row0))};
-    RowIO io_in{stage_in != nullptr ? stage_in : stage, lane, io.rows_valid};
+    RowIO io{stage, lane, min(32, max(0, min(e.T, t_end) - warp_row0)), e.debug};
+    RowIO io_in{stage_in != nullptr ? stage_in : stage, lane, io.rows_valid, e.debug};
     const bool shared_tile = stage_in == nullptr || stage_in == stage;
     const bool use_res = !kSmemRes && e.residual != nullptr;
     const bool use_mrf = kMrf && (e.mrf_mode == MRF_ADD || e.mrf_mode == MRF_LAST);
@@ -454,6 +468,7 @@ __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc&
     if (kMrf) io.request(mrf_blk, e.n_total, use_mrf, mrf_cur);
     wait_acc();
     if (dbg) dbg[0] = clock64();
+    const int dbg_c0 = n_tile > 32 ? 32 : 0;
     // warp-uniform shortcuts: tiles without masked rows skip the selects, layers without an activated copy
     // (conv_pair steps, MRF accumulation) skip its math
     const bool any_masked = __any_sync(0xffffffffu, !in_len);
@@ -463,6 +478,7 @@ __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc&
         Chunk32 res_nxt, mrf_nxt;
         const bool more = c0 + 32 < n_tile;
         const bool tma_out = tm_raw != nullptr || tm_act != nullptr || tm_mrf != nullptr;
+        if (dbg && c0 == dbg_c0) dbg[1] = clock64();
         if (!kLookahead && c0 > 0) {
             io.request(res_blk + c0, e.ld_res, use_res, res_cur);
             if (kMrf) io.request(mrf_blk + c0, e.n_total, use_mrf, mrf_cur);
@@ -486,13 +502,16 @@ __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc&
         // (kEarlyBias = false where that pushes a 128-register kernel into spilling: conv_pair)
         float bs_nxt[8];
         if (kSmemBias && kEarlyBias) bias8s_early(bias_saddr + c0 * 4, bs_nxt);
-        if (dbg && c0 == 0) dbg[1] = clock64();
         __syncwarp();
         acc.load(c0, v);
-        if (dbg && c0 == 0) dbg[2] = clock64();
+        if (dbg && c0 == dbg_c0) dbg[2] = clock64();
         if (!more) acc_drained();
         Chunk32 o_raw, o_act;
         const bool want_raw = mrf_store || e.out_raw != nullptr;
+        if (kEpiDebug && (e.debug & 8)) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) o_raw.q[g] = o_act.q[g] = make_uint4(__float_as_uint(v[g]), 0, 0, 0);
+        } else
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             float r[8], m[8], bs[8], x[8];
@@ -526,27 +545,115 @@ __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc&
                 o_act.q[g] = pack8(a);
             }
         }
-        if (dbg && c0 == 0) dbg[3] = clock64();
+        long long* dbg_rel = (dbg && c0 == dbg_c0) ? dbg + 4 : nullptr;
+        if (dbg && c0 == dbg_c0) dbg[3] = clock64();
         if (mrf_store) {
-            if (tm_mrf) io.store_tma(tm_mrf, n_base + c0, warp_row0, b, o_raw);
+            if (tm_mrf) io.store_tma(tm_mrf, n_base + c0, warp_row0, b, o_raw, dbg_rel);
             else io.store(mrf_blk + c0, e.n_total, o_raw, tma_out);
         } else {
             if (e.out_raw) {
-                if (tm_raw) io.store_tma(tm_raw, n_base + c0, warp_row0, b, o_raw);
+                if (tm_raw) io.store_tma(tm_raw, n_base + c0, warp_row0, b, o_raw, dbg_rel);
                 else io.store(e.out_raw + row0 * e.ld_raw + n_base + c0, e.ld_raw, o_raw, tma_out);
             }
             if (want_act) {
-                if (tm_act) io.store_tma(tm_act, n_base + c0, warp_row0, b, o_act);
+                if (tm_act) io.store_tma(tm_act, n_base + c0, warp_row0, b, o_act, dbg_rel);
                 else io.store(e.out_act + row0 * e.ld_act + n_base + c0, e.ld_act, o_act, tma_out);
             }
         }
-        if (dbg && c0 == 0) dbg[4] = clock64();
+        if (dbg && c0 == dbg_c0) dbg[5] = clock64();
         if (kLookahead) {
             res_cur = res_nxt;
             if (kMrf) mrf_cur = mrf_nxt;
         }
     }
-    if (dbg) dbg[5] = clock64();
+    if (dbg) dbg[6] = clock64();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Act-only lean epilogue: the activated-chain vocoder launches whose ONE output is lrelu(v) through TMA stores —
+// conv_pre, the up-samplers and conv1 of every two-launch pair (kRes = false), conv2 of pairs 0 / 1 (kRes = true).
+// run_epilogue_lean decides residual / raw / activated / MRF at run time, so a launch without a residual still
+// executed the residual's unpack + inverse-lrelu + add and packed two outputs: ~290 floating-point instructions per
+// 32-column chunk where this one needs 112 (round-2 SASS count; the math was 700 of a chunk's 1900 cycles, and at two
+// epilogue warps per scheduler those cycles are issue slots). kLd2: accumulator chunk c + 1 is in flight while chunk c
+// is converted (tcgen05.ld took ~450 cycles under the other CTA's MMAs when it was waited for on the spot).
+// n_tile must be a multiple of 64 (two chunks per loop trip keep both buffers in registers).
+// ------------------------------------------------------------------------------------------------
+template <bool kRes, bool kLd2, class WaitFn, class DrainFn>
+__device__ __forceinline__ void run_epilogue_act(const EpiParams& e, uint32_t taddr, int b, int t, int n_base, int n_tile,
+                                                 WaitFn wait_acc, DrainFn acc_drained, uint8_t* stage, uint8_t* stage_in,
+                                                 const LeanPrefetch<false>& pre, uint32_t bias_saddr,
+                                                 const CUtensorMap* tm_act, long long* dbg = nullptr) {
+    const int lane = threadIdx.x & 31;
+    const int warp_row0 = t - lane;
+    const long row0 = static_cast<long>(b) * e.T + warp_row0;
+    const bool in_len = t < pre.len_rows;
+    RowIO io{stage, lane, min(32, max(0, e.T - warp_row0)), e.debug};
+    RowIO io_in{stage_in != nullptr ? stage_in : stage, lane, io.rows_valid, e.debug};
+    const bool shared_tile = stage_in == nullptr || stage_in == stage;
+    const __half* res_blk = e.residual + row0 * e.ld_res + n_base;
+    const float slope = e.act_slope;
+    const float rinv = e.res_inv;
+    Chunk32 res_cur;
+    if (kRes) res_cur = pre.res;
+    wait_acc();
+    if (dbg) dbg[0] = clock64();
+    const bool any_masked = __any_sync(0xffffffffu, !in_len);
+    float v[kLd2 ? 2 : 1][32];
+    if (kLd2) tmem_ld32_issue(taddr, v[0]);
+    auto step = [&](int c0, float (&cur)[32], float (&nxt)[32], bool more) {
+        const bool stamp = dbg != nullptr && c0 == 32;
+        if (stamp) dbg[1] = clock64();
+        Chunk32 res_nxt;
+        if (kRes) {
+            io_in.to_row(res_cur, shared_tile);
+            io.request(res_blk + c0 + 32, e.ld_res, more, res_nxt);
+        }
+        float bs_nxt[8];
+        bias8s_early(bias_saddr + c0 * 4, bs_nxt);
+        if (kLd2) {
+            tmem_ld_wait(cur);
+            if (more) tmem_ld32_issue(taddr + c0 + 32, nxt);
+        } else {
+            __syncwarp();
+            tmem_ld32(taddr + c0, cur);
+        }
+        if (!more) acc_drained();
+        if (stamp) dbg[2] = clock64();
+        Chunk32 o;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            float bs[8], a[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bs[j] = bs_nxt[j];
+            if (g < 3) bias8s_early(bias_saddr + (c0 + (g + 1) * 8) * 4, bs_nxt);
+            if (kRes) {
+                float r[8];
+                unpack8(res_cur.q[g], r);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[j] = cur[g * 8 + j] + bs[j] + fminf(r[j], r[j] * rinv);   // rinv >= 1: inverse lrelu
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[j] = cur[g * 8 + j] + bs[j];
+            }
+            if (any_masked) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[j] = in_len ? a[j] : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j], a[j] * slope);      // slope in [0, 1): == leaky-relu
+            o.q[g] = pack8(a);
+        }
+        if (stamp) dbg[3] = clock64();
+        io.store_tma(tm_act, n_base + c0, warp_row0, b, o, stamp ? dbg + 4 : nullptr);
+        if (stamp) dbg[5] = clock64();
+        if (kRes) res_cur = res_nxt;
+    };
+    for (int c0 = 0; c0 < n_tile; c0 += 64) {
+        step(c0, v[0], v[kLd2 ? 1 : 0], true);
+        step(c0 + 32, v[kLd2 ? 1 : 0], v[0], c0 + 64 < n_tile);
+    }
+    if (dbg) dbg[6] = clock64();
 }
 #endif  // __CUDACC__
 
