@@ -15,6 +15,7 @@
 //   * epilogue requests its residual / MRF rows BEFORE the accumulator is ready (epilogue.cuh)
 //
 // Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 epilogue.
+#include <cstdio>
 #include <cstdlib>
 #include <utility>
 #include <vector>
@@ -45,6 +46,7 @@ struct ConvTc2Args {
     const __half* w;
     int tma_out;       // bit 0 / 1 / 2: out_raw / out_act / mrf_buf leave through TMA stores (lean epilogue)
     int stage2;        // lean epilogue: a second set of 4 x 2 KB staging tiles (transposes) next to the output tiles
+    int in_ring;       // TMA-in epilogue: chunks of look-ahead (input tiles per warp and kind), 1 or 2
     int sbias_bytes;   // size of the parameter tile region that precedes them
     int issue_mode;    // MMA issuer: 0 generic loops, 1 straight-line K steps, 2 + the next weight stage's barrier is tested ahead
     int params_smem;   // general epilogue: [bias][ln_g][ln_b][head_w] of this N tile staged in shared memory (room permitting)
@@ -60,13 +62,13 @@ __device__ __forceinline__ void tl2_mark(const ConvTc2Args& a, int slot) {
     if (blockIdx.x < 256 && slot < 64) a.timeline[blockIdx.x * 128 + slot] = clock64();
 }
 
-// kEpi: 0 = general epilogue, 1 = lean (vocoder hot subset), 2 = lean + MRF accumulate, 3 / 4 = act-only lean without / with a
-// residual (run_epilogue_act: the activated chain's single-output launches)
+// kEpi: 0 = general epilogue, 1 = lean (vocoder hot subset), 2 = lean + MRF accumulate, 3 = act-only lean without a residual
+// (run_epilogue_act), 4..7 = TMA-in lean with a residual (run_epilogue_tma): 4 -> out_act, 5 MRF_FIRST, 6 MRF_ADD, 7 MRF_LAST
 template <int kTmemCols, int kMinBlocks, int kEpi>
 __global__ void __launch_bounds__(192, kMinBlocks)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ ConvTc2Args args,
                 const __grid_constant__ CUtensorMap tmap_raw, const __grid_constant__ CUtensorMap tmap_act,
-                const __grid_constant__ CUtensorMap tmap_mrf) {
+                const __grid_constant__ CUtensorMap tmap_mrf, const __grid_constant__ CUtensorMap tmap_res) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_u32 = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw_u32 & 1023u)) & 1023u);
@@ -88,7 +90,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
     // 4 x 2 KB staging tiles for the epilogue warps' coalesced row I/O (epilogue.cuh)
     // 1 KB aligned: the staging tiles double as TMA-store sources with the 64-byte swizzle (address-bit XOR)
-    uint8_t* smem_stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t* in_bar = reinterpret_cast<uint64_t*>(tmem_slot + 4);   // [4 warps][2]: TMA-in epilogue (kEpi >= 4)
+    uint8_t* smem_stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(in_bar + 8) + 1023) & ~static_cast<uintptr_t>(1023));
     float* sbias = reinterpret_cast<float*>(smem_stage + 4 * 2048);   // [n_tile] this N tile's bias (lean epilogue: smem broadcast)
 
     const int warp = threadIdx.x >> 5;
@@ -112,6 +115,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         for (int i = 0; i < args.b_stages; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], csize); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
         mbar_init(w_full, 1);
+        if (kEpi >= 4)
+            for (int i = 0; i < 8; ++i) mbar_init(&in_bar[i], 1);
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
@@ -340,13 +345,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         // item's accumulator is waited for, so its latency hides behind a whole tile
         constexpr bool kLean = kEpi != 0;
         constexpr bool kMrf = kEpi == 2;
-        constexpr bool kAct = kEpi == 3 || kEpi == 4;
+        constexpr bool kAct = kEpi == 3;
         LeanPrefetch<kMrf> pre_cur, pre_nxt;
-        // kEpi == 3: nothing but lens[b] travels a tile ahead
+        // kEpi >= 3: nothing but lens[b] travels a tile ahead in registers
         auto prefetch = [&](const RowIO& io, long row0, bool on, LeanPrefetch<kMrf>& p, int pb) {
-            if (kEpi == 3) p.len_rows = (on && args.epi.lens != nullptr) ? __ldg(args.epi.lens + pb) * args.epi.len_mul : 0x7fffffff;
+            if (kEpi >= 3) p.len_rows = (on && args.epi.lens != nullptr) ? __ldg(args.epi.lens + pb) * args.epi.len_mul : 0x7fffffff;
             else lean_prefetch(args.epi, io, row0, n_base, on, p, pb);
         };
+        constexpr bool kTmaIn = kEpi >= 4;
+        constexpr bool kMrfIn = kEpi == 6 || kEpi == 7;
+        constexpr bool kStoreMrf = kEpi == 5 || kEpi == 6;
+        TmaInState in_st{smem_stage + 4 * 2048 + args.sbias_bytes + q * (args.in_ring * (kMrfIn ? 4096 : 2048)), in_bar + q * 2,
+                         args.in_ring, 0};
         if (kLean && first < n_groups) {
             const int idx0 = first * csize + crank;
             const bool v0 = idx0 < args.n_work;
@@ -354,6 +364,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             const int w0 = (v0 ? (idx0 - b0 * args.groups_t) * args.rpp : args.groups_t * args.rpp) * kTileM + q * 32;
             RowIO io{stage, lane, min(32, max(0, args.T - w0))};
             prefetch(io, static_cast<long>(b0) * args.T + w0, v0, pre_cur, b0);
+            // TMA-in: the first `ring` chunks of the first tile (a dummy item's rows are out of range: zero-filled)
+            if (kTmaIn && elect_one())
+                for (int c = 0; c < args.in_ring; ++c)
+                    tma_in_issue<kMrfIn>(in_st, c, &tmap_res, &tmap_mrf, n_base + c * 32, w0, b0);
         }
         for (int p = first; p < n_groups; p += stride, ++tl_i) {
             const int idx = p * csize + crank;
@@ -393,9 +407,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     prefetch(nio, static_cast<long>(nb) * args.T + nw0, nvalid, pre_nxt, nb);
                     long long* dbg = (tl_on && args.timeline != nullptr && blockIdx.x < 256 && tl_i < 7)
                                          ? args.timeline + blockIdx.x * 128 + 64 + tl_i * 8 : nullptr;
-                    if constexpr (kAct)
-                        run_epilogue_act<kEpi == 4, kEpi == 3>(args.epi, acc.taddr, b, t, n_base, args.n_tile, wait_acc, drained, stage, stage_in,
-                                                               pre_cur, smem_u32(sbias), &tmap_act, dbg);
+                    if constexpr (kTmaIn)
+                        run_epilogue_tma<kMrfIn, kStoreMrf, !kMrfIn>(args.epi, acc.taddr, b, t, n_base, args.n_tile, wait_acc, drained, stage,
+                                                                     in_st, pre_cur.len_rows, smem_u32(sbias), kStoreMrf ? &tmap_mrf : &tmap_act,
+                                                                     &tmap_res, &tmap_mrf, p + stride < n_groups, nb, nw0, args.err_flag, dbg);
+                    else if constexpr (kAct)
+                        run_epilogue_act<false, true>(args.epi, acc.taddr, b, t, n_base, args.n_tile, wait_acc, drained, stage, stage_in,
+                                                      pre_cur, smem_u32(sbias), &tmap_act, dbg);
                     else
                     run_epilogue_lean<kMrf, true, !(kMrf && kMinBlocks >= 2)>(args.epi, acc, b, t, n_base, args.n_tile, wait_acc, drained, stage, pre_cur,
                                             0x7fffffff, smem_u32(sbias), (args.tma_out & 1) ? &tmap_raw : nullptr,
@@ -489,7 +507,8 @@ int num_sms() {
 }
 
 struct OutMaps {
-    CUtensorMap raw, act, mrf;
+    CUtensorMap raw, act, mrf, res;
+    int epi_kind;   // kEpi of the launch, chosen by conv_forward_tc2
 };
 
 template <int kCols, int kMinBlocks, int kEpi>
@@ -513,9 +532,9 @@ static int launch_two_impl(const CUtensorMap& tm, const ConvTc2Args& a, int grid
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        TTSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<kCols, kMinBlocks, kEpi>, tm, a, om.raw, om.act, om.mrf));
+        TTSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<kCols, kMinBlocks, kEpi>, tm, a, om.raw, om.act, om.mrf, om.res));
     } else {
-        conv_tc2_kernel<kCols, kMinBlocks, kEpi><<<grid, 192, smem, s>>>(tm, a, om.raw, om.act, om.mrf);
+        conv_tc2_kernel<kCols, kMinBlocks, kEpi><<<grid, 192, smem, s>>>(tm, a, om.raw, om.act, om.mrf, om.res);
     }
     count_launch();
     TTSB_CHECK_CUDA(cudaGetLastError());
@@ -528,15 +547,21 @@ static bool host_epi_is_lean(const EpiParams& e) {
 }
 template <int kCols, int kMinBlocks>
 static int launch_two(const CUtensorMap& tm, const ConvTc2Args& a, int grid, size_t smem, cudaStream_t s, const OutMaps& om) {
-    if (!host_epi_is_lean(a.epi)) return launch_two_impl<kCols, kMinBlocks, 0>(tm, a, grid, smem, s, om);
-    static const int want_act = getenv("TTSB_EPI_ACT") ? atoi(getenv("TTSB_EPI_ACT")) : 1;
-    if (want_act && a.epi.mrf_mode == MRF_NONE && a.epi.out_raw == nullptr && a.epi.out_act != nullptr && (a.tma_out & 2) &&
-        a.n_tile % 64 == 0) {
-        if (a.epi.residual == nullptr) return launch_two_impl<kCols, kMinBlocks, 3>(tm, a, grid, smem, s, om);
-        if (want_act >= 2) return launch_two_impl<kCols, kMinBlocks, 4>(tm, a, grid, smem, s, om);
+    // the act-only / TMA-in epilogues are instantiated where the vocoder's C >= 128 layers and up-samplers run
+    // (>= 128 TMEM columns, one or two CTAs per SM); conv_forward_tc2 only picks them there
+    constexpr bool kBig = kCols >= 128 && kMinBlocks <= 2;
+    switch (om.epi_kind) {
+        case 0: return launch_two_impl<kCols, kMinBlocks, 0>(tm, a, grid, smem, s, om);
+        case 2: return launch_two_impl<kCols, kMinBlocks, 2>(tm, a, grid, smem, s, om);
+        case 3: if constexpr (kBig) return launch_two_impl<kCols, kMinBlocks, 3>(tm, a, grid, smem, s, om); break;
+        case 4: if constexpr (kBig) return launch_two_impl<kCols, kMinBlocks, 4>(tm, a, grid, smem, s, om); break;
+        case 5: if constexpr (kBig) return launch_two_impl<kCols, kMinBlocks, 5>(tm, a, grid, smem, s, om); break;
+        case 6: if constexpr (kBig) return launch_two_impl<kCols, kMinBlocks, 6>(tm, a, grid, smem, s, om); break;
+        case 7: if constexpr (kBig) return launch_two_impl<kCols, kMinBlocks, 7>(tm, a, grid, smem, s, om); break;
+        default: break;
     }
-    if (a.epi.mrf_mode == MRF_NONE) return launch_two_impl<kCols, kMinBlocks, 1>(tm, a, grid, smem, s, om);
-    return launch_two_impl<kCols, kMinBlocks, 2>(tm, a, grid, smem, s, om);
+    TTSB_REQUIRE(om.epi_kind == 1, "epilogue kind not instantiated for this tile shape");
+    return launch_two_impl<kCols, kMinBlocks, 1>(tm, a, grid, smem, s, om);
 }
 
 int conv_forward_tc2(const ConvLayer& L, const ConvRuntime& rt, const __half* in, int ld_in, int B,
@@ -613,10 +638,44 @@ int conv_forward_tc2(const ConvLayer& L, const ConvRuntime& rt, const __half* in
             smem_bytes += extra;
         }
     }
-    // second staging tile set for the lean epilogue's transposes, room permitting (see run_epilogue_lean)
+    // epilogue kind (conv_tc2_kernel's kEpi)
     a.stage2 = 0;
+    a.in_ring = 0;
     a.sbias_bytes = static_cast<int>(2048 + (smem_bytes - L.smem_bytes2));
-    {
+    om.res = tm;
+    om.epi_kind = !host_epi_is_lean(epi) ? 0 : (epi.mrf_mode == MRF_NONE ? 1 : 2);
+    static const int want_act = getenv("TTSB_EPI_ACT") ? atoi(getenv("TTSB_EPI_ACT")) : 1;
+    static const int want_tma_in = getenv("TTSB_EPI_TMA_IN") ? atoi(getenv("TTSB_EPI_TMA_IN")) : 1;
+    const bool big = L.tmem_cols2 >= 128 && L.occ2 <= 2 && L.n_tile % 64 == 0 && L.rpp == 1;
+    if (om.epi_kind == 1 && want_act && big && epi.residual == nullptr && epi.out_raw == nullptr && epi.out_act != nullptr &&
+        (a.tma_out & 2))
+        om.epi_kind = 3;
+    if (om.epi_kind != 0 && om.epi_kind != 3 && want_tma_in && big && epi.residual != nullptr && epi.out_raw == nullptr &&
+        (reinterpret_cast<uintptr_t>(epi.residual) & 15) == 0 && epi.ld_res % 8 == 0 && epi.ld_res >= L.n_total) {
+        int kind = 0;
+        switch (epi.mrf_mode) {
+            case MRF_NONE: kind = (epi.out_act != nullptr && (a.tma_out & 2)) ? 4 : 0; break;
+            case MRF_FIRST: kind = (a.tma_out & 4) ? 5 : 0; break;
+            case MRF_ADD: kind = (a.tma_out & 4) ? 6 : 0; break;
+            case MRF_LAST: kind = (epi.out_act != nullptr && (a.tma_out & 2) && (a.tma_out & 4)) ? 7 : 0; break;
+        }
+        // input tiles: 4 warps x ring x (residual [, MRF]) x 2 KB, two chunks of look-ahead if they fit, else one
+        const size_t limit = std::min<size_t>(232448, 233472 / L.occ2 - 1024);
+        const size_t per_ring = 4 * 2048 * (kind >= 6 ? 2 : 1);
+        static const int max_ring = getenv("TTSB_EPI_RING") ? atoi(getenv("TTSB_EPI_RING")) : 2;
+        int ring = 0;
+        for (int r = std::min(2, max_ring); r >= 1 && ring == 0; --r)
+            if (smem_bytes + r * per_ring <= limit) ring = r;
+        if (kind != 0 && ring != 0) {
+            const CUtensorMap* t = nullptr;
+            TTSB_PROPAGATE(get_act_tensor_map(epi.residual, epi.ld_res, B, T, L.n_total, 32, 32, &t));
+            om.res = *t;
+            om.epi_kind = kind;
+            a.in_ring = ring;
+            smem_bytes += ring * per_ring;
+        }
+    }
+    if (om.epi_kind == 1 || om.epi_kind == 2) {
         static const int want_stage2 = getenv("TTSB_STAGE2") ? atoi(getenv("TTSB_STAGE2")) : 1;
         const size_t limit = std::min<size_t>(232448, 233472 / L.occ2 - 1024);
         if (want_stage2 && host_epi_is_lean(epi) && (epi.residual != nullptr || epi.mrf_mode != MRF_NONE) && a.tma_out != 0 &&
@@ -625,6 +684,11 @@ int conv_forward_tc2(const ConvLayer& L, const ConvRuntime& rt, const __half* in
             smem_bytes += 8192;
         }
     }
+    static const int verbose = getenv("TTSB_EPI_VERBOSE") ? atoi(getenv("TTSB_EPI_VERBOSE")) : 0;
+    if (verbose)
+        fprintf(stderr, "conv_tc2: cin %d n %d taps %d rows_panel %d occ %d a_slots %d b_stages %d resident %d -> epilogue kind %d ring %d stage2 %d smem %zu\n",
+                L.cin, L.n_total, L.n_taps, L.rows_panel, L.occ2, L.a_slots2, L.b_stages2, L.resident, om.epi_kind, a.in_ring, a.stage2,
+                smem_bytes);
     // CTA pairs share streamed weight tiles through TMA multicast (halves the L2->SM weight traffic that
     // bounds the C >= 128 layers); needs at least two work items per N tile
     static const int want_cluster = getenv("TTSB_CLUSTER") ? atoi(getenv("TTSB_CLUSTER")) : 2;

@@ -655,6 +655,130 @@ __device__ __forceinline__ void run_epilogue_act(const EpiParams& e, uint32_t ta
     }
     if (dbg) dbg[6] = clock64();
 }
+
+// ------------------------------------------------------------------------------------------------
+// TMA-in lean epilogue: conv2 of every two-launch pair (residual add; MRF accumulate). The residual / MRF rows of a
+// chunk arrive as 32 x 32 TMA boxes in per-warp shared-memory tiles whose 64-byte swizzle is the row-owner layout
+// (wtile_off), `ring` chunks ahead, signalled on per-warp mbarriers. What this replaces (run_epilogue_lean): four
+// LDG.128 per lane and chunk through a transposing staging tile — 12 shared-memory instructions and two warp syncs per
+// chunk and kind, 16-32 prefetch registers, and above all a scoreboard that ptxas shares between those global loads and
+// the bias LDS of the math loop, so the "look-ahead" loads were waited for inside the math of the SAME chunk (round-2
+// timelines: 1700-2400 cycles of "math" per chunk where the act-only variant needs 300).
+//   kMrfIn:    x = m + v * mrf_scale with m from the MRF buffer (MRF_ADD / MRF_LAST); else x = v * mrf_scale when
+//              kStoreMrf (MRF_FIRST), x = v otherwise; v = acc + bias + lrelu^-1(residual), row-masked
+//   kStoreMrf: x goes to the MRF buffer as it is (tm_out = its map); else lrelu(x) goes to out_act (tm_out = its map)
+// ------------------------------------------------------------------------------------------------
+struct TmaInState {
+    uint8_t* tiles;   // this warp's input tiles: ring x (residual [, MRF]) x 2 KB, 512-byte aligned
+    uint64_t* bars;   // this warp's `ring` mbarriers (arrival count 1)
+    int ring;         // chunks of look-ahead = tiles per kind: 1 or 2
+    int j;            // chunks consumed so far: slot j % ring, parity (j / ring) & 1
+};
+
+template <bool kMrfIn>
+__device__ __forceinline__ void tma_in_issue(const TmaInState& st, int slot, const CUtensorMap* tm_res, const CUtensorMap* tm_mrf,
+                                             int col, int row, int b) {
+    constexpr uint32_t kBytes = kMrfIn ? 4096u : 2048u;
+    uint8_t* dst = st.tiles + slot * kBytes;
+    mbar_expect_tx(&st.bars[slot], kBytes);
+    tma_load_3d(dst, tm_res, &st.bars[slot], col, row, b);
+    if (kMrfIn) tma_load_3d(dst + 2048, tm_mrf, &st.bars[slot], col, row, b);
+}
+
+template <bool kMrfIn, bool kStoreMrf, bool kLd2, class WaitFn, class DrainFn>
+__device__ __forceinline__ void run_epilogue_tma(const EpiParams& e, uint32_t taddr, int b, int t, int n_base, int n_tile,
+                                                 WaitFn wait_acc, DrainFn acc_drained, uint8_t* stage, TmaInState& st,
+                                                 int len_rows, uint32_t bias_saddr, const CUtensorMap* tm_out,
+                                                 const CUtensorMap* tm_res, const CUtensorMap* tm_mrf, bool nvalid, int nb,
+                                                 int nrow0, int* err_flag, long long* dbg = nullptr) {
+    const int lane = threadIdx.x & 31;
+    const int warp_row0 = t - lane;
+    const bool in_len = t < len_rows;
+    RowIO io{stage, lane, min(32, max(0, e.T - warp_row0)), e.debug};
+    const float slope = e.act_slope;
+    const float rinv = e.res_inv;
+    const float mscale = e.mrf_scale;
+    const int n_chunks = n_tile >> 5;
+    constexpr uint32_t kBytes = kMrfIn ? 4096u : 2048u;
+    wait_acc();
+    if (dbg) dbg[0] = clock64();
+    const bool any_masked = __any_sync(0xffffffffu, !in_len);
+    float v[kLd2 ? 2 : 1][32];
+    if (kLd2) tmem_ld32_issue(taddr, v[0]);
+    auto step = [&](int ci, float (&cur)[32], float (&nxt)[32], bool more) {
+        const int c0 = ci * 32;
+        const bool stamp = dbg != nullptr && ci == 1;
+        if (stamp) dbg[1] = clock64();
+        const int slot = st.ring == 2 ? (st.j & 1) : 0;
+        const uint32_t par = static_cast<uint32_t>(st.ring == 2 ? (st.j >> 1) : st.j) & 1u;
+        mbar_wait(&st.bars[slot], par, err_flag, 208);
+        const uint32_t tile_s = smem_u32(st.tiles) + slot * kBytes;
+        uint4 rq[4], mq[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) rq[u] = lds128(tile_s + wtile_off(lane, u));
+        if (kMrfIn) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) mq[u] = lds128(tile_s + 2048 + wtile_off(lane, u));
+        }
+        float bs_nxt[8];
+        bias8s_early(bias_saddr + c0 * 4, bs_nxt);
+        if (kLd2) {
+            tmem_ld_wait(cur);
+            if (more) tmem_ld32_issue(taddr + c0 + 32, nxt);
+        } else {
+            __syncwarp();
+            tmem_ld32(taddr + c0, cur);
+        }
+        if (!more) acc_drained();
+        if (stamp) dbg[2] = clock64();
+        Chunk32 o;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            float bs[8], r[8], a[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bs[j] = bs_nxt[j];
+            if (g < 3) bias8s_early(bias_saddr + (c0 + (g + 1) * 8) * 4, bs_nxt);
+            unpack8(rq[g], r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = cur[g * 8 + j] + bs[j] + fminf(r[j], r[j] * rinv);   // rinv >= 1: inverse lrelu
+            if (any_masked) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[j] = in_len ? a[j] : 0.f;
+            }
+            if (kMrfIn) {
+                float m[8];
+                unpack8(mq[g], m);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[j] = m[j] + a[j] * mscale;
+            } else if (kStoreMrf) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[j] = a[j] * mscale;
+            }
+            if (!kStoreMrf) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j], a[j] * slope);      // slope in [0, 1): == leaky-relu
+            }
+            o.q[g] = pack8(a);
+        }
+        if (stamp) dbg[3] = clock64();
+        // every lane has consumed its rows of this slot (the math above used them): refill it with chunk j + ring, which
+        // is a later chunk of this tile or an early one of the warp's next tile
+        __syncwarp();
+        if (elect_one()) {
+            const int nci = ci + st.ring;
+            if (nci < n_chunks) tma_in_issue<kMrfIn>(st, slot, tm_res, tm_mrf, n_base + nci * 32, warp_row0, b);
+            else if (nvalid) tma_in_issue<kMrfIn>(st, slot, tm_res, tm_mrf, n_base + (nci - n_chunks) * 32, nrow0, nb);
+        }
+        io.store_tma(tm_out, n_base + c0, warp_row0, b, o, stamp ? dbg + 4 : nullptr);
+        if (stamp) dbg[5] = clock64();
+        ++st.j;
+    };
+    for (int ci = 0; ci < n_chunks; ci += 2) {
+        step(ci, v[0], v[kLd2 ? 1 : 0], true);
+        step(ci + 1, v[kLd2 ? 1 : 0], v[0], ci + 2 < n_chunks);
+    }
+    if (dbg) dbg[6] = clock64();
+}
 #endif  // __CUDACC__
 
 }  // namespace ttsb

@@ -56,6 +56,14 @@ class HostSharedBuffer:
         from multiprocessing import shared_memory
         nbytes = max(4, rows * cols * 4)
         self.shm = shared_memory.SharedMemory(name=name, create=create, size=nbytes if create else 0)
+        if not create:
+            # Python < 3.13 registers an ATTACHED segment with this process's resource tracker too, which then tries to
+            # unlink the creator's segment at exit ("leaked shared_memory objects" warnings): only the creator owns it
+            try:
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self.shm._name, 'shared_memory')
+            except Exception:
+                pass
         import numpy as np
         self.array = np.ndarray((rows, cols), dtype=np.float32, buffer=self.shm.buf)
         self.tensor = torch.from_numpy(self.array)
