@@ -198,11 +198,35 @@ def per_kernel_table(ms_by_tag, model, peaks, steps):
 # ------------------------------------------------------------------------------------------------------------------
 # reference arithmetic (oracle port): CPU arm and the eager-GPU baseline
 # ------------------------------------------------------------------------------------------------------------------
+_REF_MODELS = {}
+
+
+def reference_kind():
+    """'reference' when the unmodified reference modules are vendored under oracle/_ref (oracle/make_ref.py; they travel to
+    the GPU box with the snapshot), else 'port' (the oracle restatement)."""
+    from oracle import ref_runner
+    return 'reference' if ref_runner.available() and os.environ.get('TTSB_BENCH_REF', '1') != '0' else 'port'
+
+
 def reference_step(fsd, gsd_folded, ids, dtype=None, batched_vocoder=False):
-    """The reference's path restated (oracle/): FastPitch.infer on the padded batch, then the generator once per utterance
+    """The reference's path: FastPitch.infer on the padded batch, then the generator once per utterance
     (models/fastpitch/networks.py:322-350) — or once over the padded batch (`batched_vocoder`, what a user would write to
-    help cuDNN; padded frames then differ from the per-utterance result, so it is a throughput-only variant)."""
+    help cuDNN; padded frames then differ from the per-utterance result, so it is a throughput-only variant).
+    Runs the UNMODIFIED reference modules (oracle/_ref, same seeded synthetic checkpoints) when they are present, else the
+    oracle restatement over the state dicts passed in."""
     import torch
+    if reference_kind() == 'reference':
+        from oracle import ref_runner
+        from tts_arabic_pytorch_b200.utils import synth
+        key = (str(ids.device), dtype or torch.float32)
+        if key not in _REF_MODELS:
+            _REF_MODELS.clear()                      # one resident copy: the eager-GPU leg walks dtypes one after another
+            _REF_MODELS[key] = ref_runner.build_models(synth.fastpitch_state_dict(1234), synth.FASTPITCH_CONFIG,
+                                                       synth.hifigan_state_dict(1235), synth.HIFIGAN_CONFIG,
+                                                       device=ids.device, dtype=key[1])
+        fp, voc = _REF_MODELS[key]
+        n, wavs = ref_runner.step(fp, voc, ids, batched_vocoder)
+        return n, (wavs[0] if batched_vocoder else wavs)
     from oracle import fastpitch_oracle as fpo
     from oracle import hifigan_oracle as hgo
     from tts_arabic_pytorch_b200.utils import synth
@@ -234,7 +258,7 @@ def eager_gpu_baseline(dev, fsd, gsd_folded, ids_dev, budget_s=25.0):
     """The reference arithmetic as PyTorch eager on this GPU (cuDNN convs, cuBLAS GEMMs): fp32 (TF32 convs, torch's
     default) and fp16, vocoder per utterance as the reference does and batched. Bounded sample, CUDA events."""
     import torch
-    out = {'kind': 'port', 'library': 'PyTorch eager %s (cuDNN/cuBLAS)' % torch.__version__,
+    out = {'kind': reference_kind(), 'library': 'PyTorch eager %s (cuDNN/cuBLAS)' % torch.__version__,
            'sample': '%d x %d phonemes' % tuple(ids_dev.shape), 'unit': 'samples/s'}
     t_start = time.perf_counter()
     for name, dtype in (('fp16', torch.float16), ('fp32', torch.float32)):
@@ -279,7 +303,7 @@ def cpu_baseline(fsd, gsd_folded, ids_host, cores, cpu_sample, label):
         n += reference_step(fsd, gsd_folded, ids)[0]
         reps += 1
     dt = time.perf_counter() - t0
-    return {'value': n / dt, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+    return {'value': n / dt, 'unit': 'samples/s', 'cores': cores, 'kind': reference_kind(),
             'sample': '%d x %d utterances x %d phonemes, fp32 torch CPU (%s)' % (reps, bs, ids.shape[1], label)}
 
 
@@ -294,13 +318,24 @@ def run_reference(args):
     gsd = synth.fold_weight_norm(synth.hifigan_state_dict(1235))
     gen = torch.Generator().manual_seed(0)
     cfgname = args.config
+    kind = 'port'      # c4 (Tacotron2 lives in torchaudio, not vendored): the oracle restatement
     if cfgname == 'c2':
         from oracle import hifigan_oracle as hgo
         mel = torch.clamp(torch.randn(1, 80, 512, generator=gen) * 2 - 5, -11.5129, 2.0)
 
-        def step():
-            with torch.no_grad():
-                return int(hgo.generator_forward(gsd, synth.HIFIGAN_CONFIG, mel).numel())
+        if reference_kind() == 'reference':
+            from oracle import ref_runner
+            _, ref_voc = ref_runner.build_models(synth.fastpitch_state_dict(1234), synth.FASTPITCH_CONFIG,
+                                                 synth.hifigan_state_dict(1235), synth.HIFIGAN_CONFIG)
+
+            def step():
+                with torch.no_grad():
+                    return int(ref_voc(mel).numel())
+            kind = 'reference'
+        else:
+            def step():
+                with torch.no_grad():
+                    return int(hgo.generator_forward(gsd, synth.HIFIGAN_CONFIG, mel).numel())
         workload = 'HiFi-GAN Generator, mel [1,80,512] -> 131072 samples, host CPU'
         sample = 'the whole configuration'
     elif cfgname == 'c4':
@@ -332,6 +367,8 @@ def run_reference(args):
             ids = torch.randint(1, 40, (bs, args.phonemes), generator=gen)
             desc = '%d-phoneme' % args.phonemes
 
+        kind = reference_kind()
+
         def step():
             return reference_step(fsd, gsd, ids)[0]
         workload = ('FastPitch2Wave end-to-end, %s synthetic utterances (4 frames/phoneme), bounded sample of %d utterances '
@@ -351,7 +388,7 @@ def run_reference(args):
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
         'config': {'workload': workload, 'name': cfgname, 'phonemes': args.phonemes, 'sample_batch': args.cpu_sample or None},
         'rtf': (dt / (n / SR)),
-        'cpu_baseline': {'value': v, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+        'cpu_baseline': {'value': v, 'unit': 'samples/s', 'cores': cores, 'kind': kind,
                          'sample': '%d steps x %s' % (args.steps, sample)},
         'e2e': {'value': v, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }

@@ -29,7 +29,7 @@ def test_reference_arm_prints_one_contract_line():
     assert d['impl'] == 'reference' and d['metric'] == 'audio_samples_per_sec' and d['unit'] == 'samples/s'
     assert d['higher_is_better'] is True and d['vs_baseline'] is None and d['data'] == 'synthetic'
     assert d['value'] > 0 and d['steps'] == 1 and d['n_gpus'] == 1
-    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    assert d['cpu_baseline']['kind'] in ('reference', 'port') and d['cpu_baseline']['cores'] >= 1   # 'reference' where oracle/_ref is built
     assert d['cpu_baseline']['value'] == d['value']
     assert d['e2e'] == {'value': d['value'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert 'workload' in d['config']

@@ -148,3 +148,42 @@ def test_denoiser_oracle_matches_reference_fixture(golden_dir, hifigan_weights):
             ref = g['out%s_s%g' % (name, s)]
             assert out.shape == ref.shape
             assert np.abs(out - ref).max() < 1e-5
+
+
+def test_vendored_reference_modules_agree_with_the_oracle_port():
+    """oracle/_ref (oracle/make_ref.py: byte-for-byte copies of the reference's FastPitch / HiFi-GAN modules, git-ignored)
+    is what bench.py times as the reference arm; where it is present it must be the unmodified files and agree with the
+    restatement the parity tests use."""
+    import hashlib
+    import json
+    import os
+
+    import pytest
+    import torch
+    from oracle import fastpitch_oracle as fpo
+    from oracle import hifigan_oracle as hgo
+    from oracle import ref_runner
+    from tts_arabic_pytorch_b200.utils import synth
+
+    if not ref_runner.available():
+        pytest.skip('oracle/_ref not built (python oracle/make_ref.py needs /root/reference)')
+    root = os.path.join(os.path.dirname(os.path.abspath(ref_runner.__file__)), '_ref')
+    manifest = json.load(open(os.path.join(root, 'MANIFEST.json')))
+    for rel, meta in manifest.items():
+        with open(os.path.join(root, rel), 'rb') as fh:
+            assert hashlib.sha256(fh.read()).hexdigest() == meta['sha256'], rel
+        src = os.path.join('/root/reference', meta['source'])
+        if os.path.exists(src):
+            with open(src, 'rb') as fh:
+                assert hashlib.sha256(fh.read()).hexdigest() == meta['sha256'], 'differs from the reference: ' + rel
+    fsd, gsd = synth.fastpitch_state_dict(1234), synth.hifigan_state_dict(1235)
+    fp, voc = ref_runner.build_models(fsd, synth.FASTPITCH_CONFIG, gsd, synth.HIFIGAN_CONFIG)
+    g = torch.Generator().manual_seed(3)
+    ids = torch.randint(1, 40, (2, 14), generator=g)
+    ids[1, 9:] = 0
+    n, wavs = ref_runner.step(fp, voc, ids)
+    mel, lens, *_ = fpo.fastpitch_infer(fsd, synth.FASTPITCH_CONFIG, ids)
+    port = hgo.vocode_batch(synth.fold_weight_norm(gsd), synth.HIFIGAN_CONFIG, mel, lens)
+    assert n == sum(int(w.numel()) for w in port)
+    for a, b in zip(wavs, port):
+        assert float((a.flatten() - b.flatten()).abs().max()) < 2e-4

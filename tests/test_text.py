@@ -87,3 +87,26 @@ def test_word_cache_is_transparent():
     assert phonetiser.word_to_phones(">als~alAmu") == ph[:-1]
     assert text.buckwalter_to_tokens(line) == cold
     assert phonetiser._word_to_phones_cached.cache_info().hits > 0
+
+
+def test_vowelizer_plugin_is_applied_where_the_reference_applies_it():
+    """networks.py:75-85: the vowelizer sees the Arabic-script sentence before tokenisation; registered objects are
+    memoised per sentence; unregistered names fail loudly."""
+    import pytest
+    from tts_arabic_pytorch_b200.models.fastpitch import networks as nw
+
+    calls = []
+
+    class Upper:
+        def predict(self, s):
+            calls.append(s)
+            return s
+
+    nw.register_vowelizer('unit_test_vowelizer', Upper())
+    v = nw._load_vowelizer('unit_test_vowelizer', {})
+    assert v.predict('abc') == 'abc' and v.predict('abc') == 'abc'
+    assert calls == ['abc']
+    nw.register_vowelizer('unit_test_factory', lambda cfg: Upper())
+    assert nw._load_vowelizer('unit_test_factory', {}).predict('x') == 'x'
+    with pytest.raises(NotImplementedError):
+        nw._load_vowelizer('shakkala', {})

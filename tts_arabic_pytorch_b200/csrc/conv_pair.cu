@@ -521,7 +521,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 // 128-register budget, and a spilled load result is waited for on the spot (an L2 round trip per item).
                 // Shared-memory residual: only lens[b] is fetched, a tile ahead.
                 if (kSmemRes) prefetch(nio, static_cast<long>(nb) * args.T + nw0, nvalid, pre_nxt, nb);
-                run_epilogue_lean<kMrf, true, !kMrf, kSmemRes, kSmemRes>(args.epi, acc, b, t, 0, C, wait_acc, drained, stage, pre_cur,
+                run_epilogue_lean<kMrf, true, !kMrf, kSmemRes, kSmemRes, kEpi == 3>(args.epi, acc, b, t, 0, C, wait_acc, drained, stage, pre_cur,
                                         t0 + args.m_out, smem_u32(sbias2), nullptr, nullptr, nullptr, nullptr, dbg, res_saddr, res_phase);
                 if (!kSmemRes) prefetch(nio, static_cast<long>(nb) * args.T + nw0, nvalid, pre_nxt, nb);
             }
@@ -612,10 +612,16 @@ static int launch_pair_impl(const CUtensorMap& tm, const ConvPairArgs& a, int gr
     return 0;
 }
 
+// kEpi: 1 lean, 2 lean + MRF accumulate, 3 lean with ONE activated output and nothing else (the activated chain's pairs 0 / 1)
 template <int kCols>
 static int launch_pair(const CUtensorMap& tm, const ConvPairArgs& a, int grid, size_t smem, cudaStream_t s, bool mrf) {
-    if (a.smem_res)
+    static const int want_act_only = getenv("TTSB_PAIR_ACT_ONLY") ? atoi(getenv("TTSB_PAIR_ACT_ONLY")) : 1;
+    const bool act_only = want_act_only && !mrf && a.epi.out_raw == nullptr && a.epi.out_act != nullptr;
+    if (a.smem_res) {
+        if (act_only) return launch_pair_impl<kCols, 3, true>(tm, a, grid, smem, s);
         return mrf ? launch_pair_impl<kCols, 2, true>(tm, a, grid, smem, s) : launch_pair_impl<kCols, 1, true>(tm, a, grid, smem, s);
+    }
+    if (act_only) return launch_pair_impl<kCols, 3, false>(tm, a, grid, smem, s);
     return mrf ? launch_pair_impl<kCols, 2, false>(tm, a, grid, smem, s) : launch_pair_impl<kCols, 1, false>(tm, a, grid, smem, s);
 }
 

@@ -646,10 +646,19 @@ int conv_forward_tc2(const ConvLayer& L, const ConvRuntime& rt, const __half* in
     om.epi_kind = !host_epi_is_lean(epi) ? 0 : (epi.mrf_mode == MRF_NONE ? 1 : 2);
     static const int want_act = getenv("TTSB_EPI_ACT") ? atoi(getenv("TTSB_EPI_ACT")) : 1;
     static const int want_tma_in = getenv("TTSB_EPI_TMA_IN") ? atoi(getenv("TTSB_EPI_TMA_IN")) : 1;
-    const bool big = L.tmem_cols2 >= 128 && L.occ2 <= 2 && L.n_tile % 64 == 0 && L.rpp == 1;
-    if (om.epi_kind == 1 && want_act && big && epi.residual == nullptr && epi.out_raw == nullptr && epi.out_act != nullptr &&
-        (a.tma_out & 2))
-        om.epi_kind = 3;
+    const bool big3 = L.tmem_cols2 >= 128 && L.occ2 <= 2 && L.n_tile % 64 == 0;
+    const bool big = big3 && L.rpp == 1;
+    if (om.epi_kind == 1 && want_act && big3 && epi.residual == nullptr) {
+        if (epi.out_raw == nullptr && epi.out_act != nullptr && (a.tma_out & 2)) {
+            om.epi_kind = 3;
+        } else if (epi.out_act == nullptr && epi.out_raw != nullptr && (a.tma_out & 1)) {
+            // a raw-only output is the activated one with slope 1: max(v, 1 * v) == v exactly
+            a.epi.out_act = epi.out_raw; a.epi.ld_act = epi.ld_raw; a.epi.act_slope = 1.f; a.epi.out_raw = nullptr;
+            om.act = om.raw;
+            a.tma_out = 2;
+            om.epi_kind = 3;
+        }
+    }
     if (om.epi_kind != 0 && om.epi_kind != 3 && want_tma_in && big && epi.residual != nullptr && epi.out_raw == nullptr &&
         (reinterpret_cast<uintptr_t>(epi.residual) & 15) == 0 && epi.ld_res % 8 == 0 && epi.ld_res >= L.n_total) {
         int kind = 0;
@@ -666,6 +675,17 @@ int conv_forward_tc2(const ConvLayer& L, const ConvRuntime& rt, const __half* in
         int ring = 0;
         for (int r = std::min(2, max_ring); r >= 1 && ring == 0; --r)
             if (smem_bytes + r * per_ring <= limit) ring = r;
+        // no room: give up the fourth weight stage (the layers whose plan has three run the same main loop)
+        static const int may_trade = getenv("TTSB_EPI_TRADE_B") ? atoi(getenv("TTSB_EPI_TRADE_B")) : 1;
+        if (kind != 0 && ring == 0 && may_trade && !L.resident && a.b_stages >= 4) {
+            const size_t btile = static_cast<size_t>(L.n_tile) * L.chunk_k * 2;
+            for (int r = std::min(2, max_ring); r >= 1 && ring == 0; --r)
+                if (smem_bytes - btile + r * per_ring <= limit) ring = r;
+            if (ring != 0) {
+                a.b_stages -= 1;
+                smem_bytes -= btile;
+            }
+        }
         if (kind != 0 && ring != 0) {
             const CUtensorMap* t = nullptr;
             TTSB_PROPAGATE(get_act_tensor_map(epi.residual, epi.ld_res, B, T, L.n_total, 32, 32, &t));

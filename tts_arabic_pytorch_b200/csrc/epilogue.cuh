@@ -425,8 +425,8 @@ __device__ __forceinline__ void lean_prefetch(const EpiParams& e, const RowIO& i
 // kMrf = false: mrf_mode == MRF_NONE is guaranteed by the caller.
 // kLookahead = false (register-starved variants): a chunk's residual / MRF rows are requested when the chunk
 // starts, not one chunk ahead.
-template <bool kMrf, bool kSmemBias = false, bool kLookahead = true, bool kEarlyBias = true, bool kSmemRes = false, class Acc,
-          class WaitFn, class DrainFn>
+template <bool kMrf, bool kSmemBias = false, bool kLookahead = true, bool kEarlyBias = true, bool kSmemRes = false,
+          bool kActOnly = false, class Acc, class WaitFn, class DrainFn>
 __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc& acc, int b, int t, int n_base,
                                                   int n_tile, WaitFn wait_acc, DrainFn acc_drained, uint8_t* stage,
                                                   const LeanPrefetch<kMrf>& pre, int t_end = 0x7fffffff,
@@ -472,7 +472,8 @@ __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc&
     // warp-uniform shortcuts: tiles without masked rows skip the selects, layers without an activated copy
     // (conv_pair steps, MRF accumulation) skip its math
     const bool any_masked = __any_sync(0xffffffffu, !in_len);
-    const bool want_act = e.out_act != nullptr && !mrf_store;
+    // kActOnly (caller guarantees: no MRF, no raw output, an activated output): the output selection is compile-time
+    const bool want_act = kActOnly || (e.out_act != nullptr && !mrf_store);
     for (int c0 = 0; c0 < n_tile; c0 += 32) {
         float v[32];
         Chunk32 res_nxt, mrf_nxt;
@@ -507,7 +508,7 @@ __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc&
         if (dbg && c0 == dbg_c0) dbg[2] = clock64();
         if (!more) acc_drained();
         Chunk32 o_raw, o_act;
-        const bool want_raw = mrf_store || e.out_raw != nullptr;
+        const bool want_raw = !kActOnly && (mrf_store || e.out_raw != nullptr);
         if (kEpiDebug && (e.debug & 8)) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) o_raw.q[g] = o_act.q[g] = make_uint4(__float_as_uint(v[g]), 0, 0, 0);
@@ -551,7 +552,7 @@ __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc&
             if (tm_mrf) io.store_tma(tm_mrf, n_base + c0, warp_row0, b, o_raw, dbg_rel);
             else io.store(mrf_blk + c0, e.n_total, o_raw, tma_out);
         } else {
-            if (e.out_raw) {
+            if (!kActOnly && e.out_raw) {
                 if (tm_raw) io.store_tma(tm_raw, n_base + c0, warp_row0, b, o_raw, dbg_rel);
                 else io.store(e.out_raw + row0 * e.ld_raw + n_base + c0, e.ld_raw, o_raw, tma_out);
             }
@@ -720,13 +721,23 @@ __device__ __forceinline__ void run_epilogue_tma(const EpiParams& e, uint32_t ta
 #pragma unroll
             for (int u = 0; u < 4; ++u) mq[u] = lds128(tile_s + 2048 + wtile_off(lane, u));
         }
+        // Every lane's ld.shared of this slot has been issued (they complete within tens of cycles; a TMA write cannot land
+        // in less than several hundred): refill the slot with chunk j + ring — a later chunk of this tile or an early one
+        // of the warp's next tile — BEFORE this chunk's math, so the copy has the math, the store and (ring = 2) a whole
+        // further chunk to arrive (issued after the math it was still 1200-1900 cycles late: round-2 session 17)
+        __syncwarp();
+        if (elect_one()) {
+            const int nci = ci + st.ring;
+            if (nci < n_chunks) tma_in_issue<kMrfIn>(st, slot, tm_res, tm_mrf, n_base + nci * 32, warp_row0, b);
+            else if (nvalid) tma_in_issue<kMrfIn>(st, slot, tm_res, tm_mrf, n_base + (nci - n_chunks) * 32, nrow0, nb);
+        }
+        __syncwarp();      // the tcgen05.ld / wait below are .sync.aligned: the elected lane must be back with the others
         float bs_nxt[8];
         bias8s_early(bias_saddr + c0 * 4, bs_nxt);
         if (kLd2) {
             tmem_ld_wait(cur);
             if (more) tmem_ld32_issue(taddr + c0 + 32, nxt);
         } else {
-            __syncwarp();
             tmem_ld32(taddr + c0, cur);
         }
         if (!more) acc_drained();
@@ -761,14 +772,6 @@ __device__ __forceinline__ void run_epilogue_tma(const EpiParams& e, uint32_t ta
             o.q[g] = pack8(a);
         }
         if (stamp) dbg[3] = clock64();
-        // every lane has consumed its rows of this slot (the math above used them): refill it with chunk j + ring, which
-        // is a later chunk of this tile or an early one of the warp's next tile
-        __syncwarp();
-        if (elect_one()) {
-            const int nci = ci + st.ring;
-            if (nci < n_chunks) tma_in_issue<kMrfIn>(st, slot, tm_res, tm_mrf, n_base + nci * 32, warp_row0, b);
-            else if (nvalid) tma_in_issue<kMrfIn>(st, slot, tm_res, tm_mrf, n_base + (nci - n_chunks) * 32, nrow0, nb);
-        }
         io.store_tma(tm_out, n_base + c0, warp_row0, b, o, stamp ? dbg + 4 : nullptr);
         if (stamp) dbg[5] = clock64();
         ++st.j;

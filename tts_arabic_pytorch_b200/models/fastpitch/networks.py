@@ -37,10 +37,46 @@ def pitch_trf(mul: float = 1, add: float = 0):
     return _apply
 
 
+# The reference's `load_vowelizer` (models/diacritizers/__init__.py:4-12) builds one of two char-level BiLSTM diacritizers
+# (shakkala, shakkelha). Those models are outside the hot path this package implements, but the
+# text pre-step they plug into is part of the API (networks.py:75-85): any object with `predict(arabic_text) -> str` can be
+# registered under the reference's names (e.g. the reference's own model objects) and is then used exactly where the
+# reference uses them; predictions are memoised per sentence (the front-end is what a batch waits
+# for at 10^4 x real time).
+_VOWELIZERS = {}
+
+
+class _CachedVowelizer:
+    def __init__(self, model, max_entries=65536):
+        self.model = model
+        self.cache = {}
+        self.max_entries = max_entries
+
+    def predict(self, utterance: str) -> str:
+        hit = self.cache.get(utterance)
+        if hit is None:
+            hit = self.model.predict(utterance)
+            if len(self.cache) >= self.max_entries:
+                self.cache.clear()
+            self.cache[utterance] = hit
+        return hit
+
+
+def register_vowelizer(name: str, model_or_factory):
+    """Make `vowelizer=name` available: `model_or_factory` is an object with predict(str) -> str, or a callable
+    (config) -> such an object that is invoked on first use (the reference loads its diacritizers lazily too)."""
+    _VOWELIZERS[name] = model_or_factory
+
+
 def _load_vowelizer(name, config):
-    raise NotImplementedError(
-        "vowelizer '%s': the diacritizer RNNs are outside the hot path this package implements "
-        '(SURVEY.md §2 row 12); pass already-vocalised text' % name)
+    if name not in _VOWELIZERS:
+        raise NotImplementedError(
+            "vowelizer '%s' is not registered: the diacritizer RNNs are outside the hot path this package implements "
+            "(SURVEY.md §2 row 12). Pass already-vocalised text, or plug a model in with "
+            "tts_arabic_pytorch_b200.models.fastpitch.networks.register_vowelizer(name, obj_with_predict)" % name)
+    entry = _VOWELIZERS[name]
+    model = entry if hasattr(entry, 'predict') else entry(config)
+    return _CachedVowelizer(model)
 
 
 class FastPitch(_FastPitch):
