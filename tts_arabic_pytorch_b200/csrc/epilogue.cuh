@@ -721,10 +721,14 @@ __device__ __forceinline__ void run_epilogue_tma(const EpiParams& e, uint32_t ta
 #pragma unroll
             for (int u = 0; u < 4; ++u) mq[u] = lds128(tile_s + 2048 + wtile_off(lane, u));
         }
-        // Every lane's ld.shared of this slot has been issued (they complete within tens of cycles; a TMA write cannot land
-        // in less than several hundred): refill the slot with chunk j + ring — a later chunk of this tile or an early one
-        // of the warp's next tile — BEFORE this chunk's math, so the copy has the math, the store and (ring = 2) a whole
-        // further chunk to arrive (issued after the math it was still 1200-1900 cycles late: round-2 session 17)
+        // Refill the slot with chunk j + ring — a later chunk of this tile or an early one of the warp's next tile —
+        // BEFORE this chunk's math, so the copy has the math, the store and (ring = 2) a whole further chunk to arrive
+        // (issued after the math it was still 1200-1900 cycles late: round-2 session 17). The TMA write must not overtake
+        // the ld.shared above: "issued" is not "performed" — under the MMAs' operand traffic a shared-memory load can sit
+        // in the queue longer than an L2-hit TMA copy takes (session 19: sparse corruption without the fence). The proxy
+        // fence (MEMBAR.CTA + async-proxy fence) retires this lane's loads and orders them before the async-proxy write;
+        // nothing else is outstanding here, so it is cheap. The warp sync extends that to all 32 lanes.
+        fence_proxy_async();
         __syncwarp();
         if (elect_one()) {
             const int nci = ci + st.ring;

@@ -111,6 +111,11 @@ def synthesize(model, id_list: List[torch.Tensor], speed=1., speaker_id=0, denoi
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
         return t_local + 1 if t_local < int(t[0]) else t_local
 
+    if world == 1 and deliver != 'nccl':
+        # one rank, host delivery: FastPitch2Wave.synthesize_ids itself (its device -> host copies run under the generator)
+        wavs, _ = model.synthesize_ids(id_list, speed, speaker_id, denoise, pitch_transform, max_duration, to_cpu=True)
+        stats = {'frames': sum(int(w.numel()) for w in wavs) // max(1, model.vocoder.hop), 'utterances': len(wavs)}
+        return (wavs, stats) if return_stats else wavs
     if mine:
         wav, n_samples, inverse, _ = model.synthesize_ids([id_list[i] for i in mine], speed, speaker_id, denoise,
                                                           pitch_transform, max_duration, to_cpu=False,

@@ -10,6 +10,7 @@ Extra (not in the reference): forward(x, lens=...) masks every layer at each utt
 length so a padded batch equals the reference's per-utterance loop.
 """
 import ctypes
+import os
 
 import torch
 import torch.nn as nn
@@ -143,10 +144,14 @@ class Generator(nn.Module):
     def _device(self):
         return self.conv_post.bias.device
 
-    def run(self, mel_f32=None, mel_cl=None, lens=None, lens_host=None):
+    def run(self, mel_f32=None, mel_cl=None, lens=None, lens_host=None, host_out=None):
         """Padded batch -> [B, T*hop] fp32. `mel_f32` [B,80,T] or `mel_cl` [B,T,128] fp16. lens_host: the frame counts as a
         Python list when the caller already has them on the host (FastPitch.infer attaches them to the `dec_lens` it
-        returns): the padded batch then runs in chunks at each chunk's own longest utterance (ttsb_hifigan_forward)."""
+        returns): the padded batch then runs in chunks at each chunk's own longest utterance (ttsb_hifigan_forward).
+        host_out: a pinned [B, T*hop] fp32 host tensor. The batch then runs in groups of utterances (one workspace chunk
+        each) and every finished group is copied device -> host on a side stream while the next group computes, so the
+        134 MB of a 256-utterance batch leave over PCIe under the generator instead of after it; the call returns once
+        the last copy has landed."""
         device = self._device()
         if device.type != 'cuda':
             raise RuntimeError('tts_arabic_pytorch_b200 has no CPU path: move the vocoder to a CUDA device '
@@ -171,8 +176,33 @@ class Generator(nn.Module):
             wav = torch.empty(B, T * self.hop, dtype=torch.float32, device=device)
             nbytes = lib.ttsb_hifigan_workspace_bytes(handle, B, T)
             ws = self._ws.get(nbytes, device)
-            _lib.check(lib.ttsb_hifigan_forward(handle, _lib.ptr(mel_f32), _lib.ptr(mel_cl), _lib.ptr(lens), h_lens, B, T,
-                                                _lib.ptr(wav), _lib.ptr(ws), nbytes, _lib.current_stream(device)))
+            group = B
+            if host_out is not None:
+                assert host_out.shape == wav.shape and host_out.dtype == torch.float32 and host_out.is_pinned()
+                group = max(1, min(B, int(os.environ.get('TTSB_D2H_GROUP_FRAMES', '32768')) // max(T, 1)))
+            if group >= B and host_out is None:
+                _lib.check(lib.ttsb_hifigan_forward(handle, _lib.ptr(mel_f32), _lib.ptr(mel_cl), _lib.ptr(lens), h_lens, B, T,
+                                                    _lib.ptr(wav), _lib.ptr(ws), nbytes, _lib.current_stream(device)))
+            else:
+                copy_stream = self.__dict__.get('_copy_stream')
+                if copy_stream is None or copy_stream.device != device:
+                    copy_stream = self.__dict__['_copy_stream'] = torch.cuda.Stream(device=device)
+                main = torch.cuda.current_stream(device)
+                for b0 in range(0, B, group):
+                    b1 = min(B, b0 + group)
+                    sub_lens = None if h_lens is None else (ctypes.c_int32 * (b1 - b0))(*h_lens[b0:b1])
+                    _lib.check(lib.ttsb_hifigan_forward(
+                        handle, _lib.ptr(mel_f32[b0:b1]) if mel_f32 is not None else None,
+                        _lib.ptr(mel_cl[b0:b1]) if mel_cl is not None else None,
+                        _lib.ptr(lens[b0:b1]) if lens is not None else None, sub_lens, b1 - b0, T, _lib.ptr(wav[b0:b1]),
+                        _lib.ptr(ws), nbytes, _lib.current_stream(device)))
+                    done = torch.cuda.Event()
+                    done.record(main)
+                    copy_stream.wait_event(done)
+                    with torch.cuda.stream(copy_stream):
+                        host_out[b0:b1].copy_(wav[b0:b1], non_blocking=True)
+                wav.record_stream(copy_stream)
+                copy_stream.synchronize()
         del src
         return wav
 
