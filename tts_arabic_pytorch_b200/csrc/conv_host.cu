@@ -137,7 +137,13 @@ int conv_layer_create(ConvLayer& L, int cin_logical, int cin_stored, int n_total
         const size_t w_all = static_cast<size_t>(total_b) * btile;
         const int min_a = std::min(L.n_chunks, 2);
         const size_t third = kSmemMax / 3 - 2048;
-        const bool can2 = min_a * panel + 2 * btile + bar_bytes <= half && n_tile <= 256;
+        // A layer whose ONE N tile is 256 columns wide (the C = 256 ResBlock convs) gets a single accumulator buffer in half
+        // of the TMEM, so a two-CTA plan serialises its MMAs and its epilogue inside each CTA, with two panels and two
+        // weight stages: one CTA per SM (double-buffered accumulator, 4 + 4 ring slots, room for the TMA-in epilogue tiles)
+        // measured 65 vs 86 us on the k = 3 conv2 (profiles/r02_s22_occupancy.txt). Layers with several N tiles (the
+        // up-samplers, conv-FF) keep two CTAs: there the second CTA works on another N tile of the same rows.
+        const bool single_wide_tile = n_tile == 256 && n_total == n_tile;
+        const bool can2 = min_a * panel + 2 * btile + bar_bytes <= half && n_tile <= 256 && !single_wide_tile;
         const bool can3 = min_a * panel + std::min(3, total_b) * btile + bar_bytes <= third && 2 * n_tile <= 128;
         L.occ2 = can2 ? 2 : 1;
         if (const char* e = getenv("TTSB_OCC2")) L.occ2 = std::max(1, std::min(atoi(e), can3 ? 3 : (can2 ? 2 : 1)));

@@ -665,7 +665,8 @@ int conv_pair_forward(const ConvLayer& L1, const ConvLayer& L2, const ConvPairPl
     // shared-memory residual: activated input (the panel holds what the residual add needs), one channel chunk, and an x
     // ring deep enough to keep a panel until its item's final epilogue (producer -> conv1 -> mid -> conv2 -> final)
     static const int want_smem_res = getenv("TTSB_PAIR_SMEM_RES") ? atoi(getenv("TTSB_PAIR_SMEM_RES")) : 1;
-    a.smem_res = (want_smem_res && in_act && L1.n_chunks == 1 && plan.x_slots >= 5) ? 1 : 0;
+    static const int smem_res_min_slots = getenv("TTSB_PAIR_SMEM_RES_SLOTS") ? atoi(getenv("TTSB_PAIR_SMEM_RES_SLOTS")) : 5;
+    a.smem_res = (want_smem_res && in_act && L1.n_chunks == 1 && plan.x_slots >= smem_res_min_slots) ? 1 : 0;
     const int grid = std::min(num_sms(), a.n_work);
     const bool mrf = epi.mrf_mode != MRF_NONE;
     switch (plan.tmem_cols) {
