@@ -646,8 +646,8 @@ int conv_forward_tc2(const ConvLayer& L, const ConvRuntime& rt, const __half* in
     om.epi_kind = !host_epi_is_lean(epi) ? 0 : (epi.mrf_mode == MRF_NONE ? 1 : 2);
     static const int want_act = getenv("TTSB_EPI_ACT") ? atoi(getenv("TTSB_EPI_ACT")) : 1;
     static const int want_tma_in = getenv("TTSB_EPI_TMA_IN") ? atoi(getenv("TTSB_EPI_TMA_IN")) : 1;
-    const bool big3 = L.tmem_cols2 >= 128 && L.occ2 <= 2 && L.n_tile % 64 == 0;
-    const bool big = big3 && L.rpp == 1;
+    const bool big3 = L.tmem_cols2 >= 128 && L.occ2 <= 2 && L.n_tile % 32 == 0;
+    const bool big = big3 && L.rpp == 1 && L.n_tile % 64 == 0;
     if (om.epi_kind == 1 && want_act && big3 && epi.residual == nullptr) {
         if (epi.out_raw == nullptr && epi.out_act != nullptr && (a.tma_out & 2)) {
             om.epi_kind = 3;

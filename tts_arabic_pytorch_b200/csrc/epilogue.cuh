@@ -578,7 +578,7 @@ __device__ __forceinline__ void run_epilogue_lean(const EpiParams& e, const Acc&
 // 32-column chunk where this one needs 112 (round-2 SASS count; the math was 700 of a chunk's 1900 cycles, and at two
 // epilogue warps per scheduler those cycles are issue slots). kLd2: accumulator chunk c + 1 is in flight while chunk c
 // is converted (tcgen05.ld took ~450 cycles under the other CTA's MMAs when it was waited for on the spot).
-// n_tile must be a multiple of 64 (two chunks per loop trip keep both buffers in registers).
+// Two chunks per loop trip keep both accumulator buffers in registers (n_tile: any multiple of 32).
 // ------------------------------------------------------------------------------------------------
 template <bool kRes, bool kLd2, class WaitFn, class DrainFn>
 __device__ __forceinline__ void run_epilogue_act(const EpiParams& e, uint32_t taddr, int b, int t, int n_base, int n_tile,
@@ -651,8 +651,9 @@ __device__ __forceinline__ void run_epilogue_act(const EpiParams& e, uint32_t ta
         if (kRes) res_cur = res_nxt;
     };
     for (int c0 = 0; c0 < n_tile; c0 += 64) {
-        step(c0, v[0], v[kLd2 ? 1 : 0], true);
-        step(c0 + 32, v[kLd2 ? 1 : 0], v[0], c0 + 64 < n_tile);
+        const bool two = c0 + 32 < n_tile;          // n_tile is a multiple of 32: an odd chunk count ends on a single step
+        step(c0, v[0], v[kLd2 ? 1 : 0], two);
+        if (two) step(c0 + 32, v[kLd2 ? 1 : 0], v[0], c0 + 64 < n_tile);
     }
     if (dbg) dbg[6] = clock64();
 }
