@@ -220,9 +220,12 @@ def reference_step(fsd, gsd_folded, ids, dtype=None, batched_vocoder=False):
         from tts_arabic_pytorch_b200.utils import synth
         key = (str(ids.device), dtype or torch.float32)
         if key not in _REF_MODELS:
+            sds = _REF_MODELS.get('state_dicts')
+            if sds is None:
+                sds = (synth.fastpitch_state_dict(1234), synth.hifigan_state_dict(1235))
             _REF_MODELS.clear()                      # one resident copy: the eager-GPU leg walks dtypes one after another
-            _REF_MODELS[key] = ref_runner.build_models(synth.fastpitch_state_dict(1234), synth.FASTPITCH_CONFIG,
-                                                       synth.hifigan_state_dict(1235), synth.HIFIGAN_CONFIG,
+            _REF_MODELS['state_dicts'] = sds
+            _REF_MODELS[key] = ref_runner.build_models(sds[0], synth.FASTPITCH_CONFIG, sds[1], synth.HIFIGAN_CONFIG,
                                                        device=ids.device, dtype=key[1])
         fp, voc = _REF_MODELS[key]
         n, wavs = ref_runner.step(fp, voc, ids, batched_vocoder)
@@ -254,7 +257,7 @@ def _fp_infer_on(fsd, cfg, ids, dtype):
         torch.set_default_device(prev if prev is not None else 'cpu')
 
 
-def eager_gpu_baseline(dev, fsd, gsd_folded, ids_dev, budget_s=25.0):
+def eager_gpu_baseline(dev, fsd, gsd_folded, ids_dev, budget_s=60.0):
     """The reference arithmetic as PyTorch eager on this GPU (cuDNN convs, cuBLAS GEMMs): fp32 (TF32 convs, torch's
     default) and fp16, vocoder per utterance as the reference does and batched. Bounded sample, CUDA events."""
     import torch

@@ -115,18 +115,19 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         for (int i = 0; i < args.b_stages; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], csize); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
         mbar_init(w_full, 1);
-        if (kEpi >= 4)
+        if (kEpi >= 4 && kEpi <= 7)
             for (int i = 0; i < 8; ++i) mbar_init(&in_bar[i], 1);
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
-    if (kEpi != 0) {
+    if (kEpi != 0 && kEpi != 8) {
         for (int i = threadIdx.x; i < args.n_tile; i += 192)
             sbias[i] = args.epi.bias != nullptr ? args.epi.bias[ntile * args.n_tile + i] : 0.f;
     } else if (args.params_smem) {
-        const float* src[4] = {args.epi.bias, args.epi.ln_g, args.epi.ln_b, args.epi.head_w};
+        // (selects, not an indexed pointer array: that array was the kernel's only stack frame)
         for (int i = threadIdx.x; i < 4 * args.n_tile; i += 192) {
-            const float* p = src[i / args.n_tile];
+            const int which = i / args.n_tile;
+            const float* p = which == 0 ? args.epi.bias : (which == 1 ? args.epi.ln_g : (which == 2 ? args.epi.ln_b : args.epi.head_w));
             sbias[i] = p != nullptr ? p[ntile * args.n_tile + i % args.n_tile] : 0.f;
         }
     }
@@ -343,7 +344,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         uint8_t* stage_in = args.stage2 ? smem_stage + 4 * 2048 + args.sbias_bytes + q * 2048 : nullptr;
         // lean path: the first residual / MRF chunk of the NEXT work item is requested before this
         // item's accumulator is waited for, so its latency hides behind a whole tile
-        constexpr bool kLean = kEpi != 0;
+        constexpr bool kLean = kEpi != 0 && kEpi != 8;
         constexpr bool kMrf = kEpi == 2;
         constexpr bool kAct = kEpi == 3;
         LeanPrefetch<kMrf> pre_cur, pre_nxt;
@@ -352,7 +353,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             if (kEpi >= 3) p.len_rows = (on && args.epi.lens != nullptr) ? __ldg(args.epi.lens + pb) * args.epi.len_mul : 0x7fffffff;
             else lean_prefetch(args.epi, io, row0, n_base, on, p, pb);
         };
-        constexpr bool kTmaIn = kEpi >= 4;
+        constexpr bool kTmaIn = kEpi >= 4 && kEpi <= 7;
         constexpr bool kMrfIn = kEpi == 6 || kEpi == 7;
         constexpr bool kStoreMrf = kEpi == 5 || kEpi == 6;
         TmaInState in_st{smem_stage + 4 * 2048 + args.sbias_bytes + q * (args.in_ring * (kMrfIn ? 4096 : 2048)), in_bar + q * 2,
@@ -422,8 +423,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 } else {
                     long long* dbg = (tl_on && args.timeline != nullptr && blockIdx.x < 256 && tl_i < 7)
                                          ? args.timeline + blockIdx.x * 128 + 64 + tl_i * 8 : nullptr;
-                    run_epilogue(args.epi, acc, b, t, t < args.T, n_base, args.n_tile, wait_acc, drained, stage, dbg,
-                                 args.params_smem ? smem_u32(sbias) : 0u);
+                    run_epilogue<kEpi == 8 ? 1 : 0>(args.epi, acc, b, t, t < args.T, n_base, args.n_tile, wait_acc, drained, stage, dbg,
+                                                    args.params_smem ? smem_u32(sbias) : 0u);
                 }
             }
             if (tl_on && tl_i < 7) tl2_mark(args, 8 + tl_i * 8 + 6);
@@ -552,6 +553,7 @@ static int launch_two(const CUtensorMap& tm, const ConvTc2Args& a, int grid, siz
     constexpr bool kBig = kCols >= 128 && kMinBlocks <= 2;
     switch (om.epi_kind) {
         case 0: return launch_two_impl<kCols, kMinBlocks, 0>(tm, a, grid, smem, s, om);
+        case 8: return launch_two_impl<kCols, kMinBlocks, 8>(tm, a, grid, smem, s, om);
         case 2: return launch_two_impl<kCols, kMinBlocks, 2>(tm, a, grid, smem, s, om);
         case 3: if constexpr (kBig) return launch_two_impl<kCols, kMinBlocks, 3>(tm, a, grid, smem, s, om); break;
         case 4: if constexpr (kBig) return launch_two_impl<kCols, kMinBlocks, 4>(tm, a, grid, smem, s, om); break;
@@ -643,7 +645,7 @@ int conv_forward_tc2(const ConvLayer& L, const ConvRuntime& rt, const __half* in
     a.in_ring = 0;
     a.sbias_bytes = static_cast<int>(2048 + (smem_bytes - L.smem_bytes2));
     om.res = tm;
-    om.epi_kind = !host_epi_is_lean(epi) ? 0 : (epi.mrf_mode == MRF_NONE ? 1 : 2);
+    om.epi_kind = !host_epi_is_lean(epi) ? (epi.ln_g != nullptr ? 8 : 0) : (epi.mrf_mode == MRF_NONE ? 1 : 2);
     static const int want_act = getenv("TTSB_EPI_ACT") ? atoi(getenv("TTSB_EPI_ACT")) : 1;
     static const int want_tma_in = getenv("TTSB_EPI_TMA_IN") ? atoi(getenv("TTSB_EPI_TMA_IN")) : 1;
     const bool big3 = L.tmem_cols2 >= 128 && L.occ2 <= 2 && L.n_tile % 32 == 0;
@@ -659,7 +661,7 @@ int conv_forward_tc2(const ConvLayer& L, const ConvRuntime& rt, const __half* in
             om.epi_kind = 3;
         }
     }
-    if (om.epi_kind != 0 && om.epi_kind != 3 && want_tma_in && big && epi.residual != nullptr && epi.out_raw == nullptr &&
+    if (om.epi_kind != 0 && om.epi_kind != 8 && om.epi_kind != 3 && want_tma_in && big && epi.residual != nullptr && epi.out_raw == nullptr &&
         (reinterpret_cast<uintptr_t>(epi.residual) & 15) == 0 && epi.ld_res % 8 == 0 && epi.ld_res >= L.n_total) {
         int kind = 0;
         switch (epi.mrf_mode) {

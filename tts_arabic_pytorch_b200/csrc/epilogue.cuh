@@ -244,7 +244,11 @@ __device__ __forceinline__ void bias8s(uint32_t saddr, float (&f)[8]) {
 // of the residual / MRF rows has been requested from HBM. `acc_drained()` is called right after the
 // last read of the accumulator so a persistent kernel can hand the TMEM buffer back early.
 // `stage`: this warp's 2 KB staging tile for coalesced row I/O (null = direct access).
-template <class Acc, class WaitFn, class DrainFn>
+// kLnMode: -1 = every feature decided at run time (the check kernels), 1 = LayerNorm launches only (residual + LN,
+// relu -> LN, predictor head: no fp32 / transposed / tanh outputs), 0 = launches without LayerNorm. The two compile-time
+// forms exist because the all-in-one body needs 254 registers AND a stack frame in conv_tc2 (every spill reload is an L2
+// round trip on an SM whose L1 is carved out as shared memory).
+template <int kLnMode = -1, class Acc, class WaitFn, class DrainFn>
 __device__ __forceinline__ void run_epilogue(const EpiParams& e, const Acc& acc, int b, int t,
                                              bool row_ok, int n_base, int n_tile, WaitFn wait_acc,
                                              DrainFn acc_drained, uint8_t* stage = nullptr,
@@ -257,10 +261,11 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& e, const Acc& acc,
     const long row = row0 + lane;
     bool in_len = true;
     if (e.lens != nullptr && row_ok) in_len = t < e.lens[b] * e.len_mul;
-    const bool do_ln = e.ln_g != nullptr;
+    const bool do_ln = kLnMode < 0 ? e.ln_g != nullptr : kLnMode == 1;
+    constexpr bool kNoLnOutputs = kLnMode == 1;     // LayerNorm launches write raw / activated fp16 rows and the head only
     RowIO io{stage, lane, min(32, max(0, e.T - warp_row0))};
     const bool use_res = e.residual != nullptr;
-    const bool use_mrf = e.mrf_mode == MRF_ADD || e.mrf_mode == MRF_LAST;
+    const bool use_mrf = !kNoLnOutputs && (e.mrf_mode == MRF_ADD || e.mrf_mode == MRF_LAST);
     const __half* res_blk = e.residual + row0 * e.ld_res + n_base;
     __half* mrf_blk = e.mrf_buf + row0 * e.n_total + n_base;
 
@@ -337,7 +342,7 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& e, const Acc& acc,
                 param8(2, e.ln_b, n, bt);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) x[j] = (v[g * 8 + j] - mean) * rstd * gm[j] + bt[j];
-                if (e.head_w) {
+                if (kLnMode != 0 && e.head_w) {
                     float hw[8];
                     param8(3, e.head_w, n, hw);
 #pragma unroll
@@ -350,7 +355,7 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& e, const Acc& acc,
 #pragma unroll
                 for (int j = 0; j < 8; ++j) x[j] = v[g * 8 + j] + bs[j] + fminf(r[j], r[j] * e.res_inv);
             }
-            if (e.out_f32_t && e.f32_unmasked && row_ok) {
+            if (!kNoLnOutputs && e.out_f32_t && e.f32_unmasked && row_ok) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     if (n + j < e.n_store)
@@ -360,7 +365,7 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& e, const Acc& acc,
 #pragma unroll
                 for (int j = 0; j < 8; ++j) x[j] = 0.f;
             }
-            if (e.mrf_mode != MRF_NONE) {
+            if (!kNoLnOutputs && e.mrf_mode != MRF_NONE) {
                 float m[8];
                 unpack8(mrf_cur.q[g], m);
 #pragma unroll
@@ -368,24 +373,24 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& e, const Acc& acc,
                 o_mrf.q[g] = pack8(x);
             }
             o_raw.q[g] = pack8(x);
-            if (e.out_f32_t && !e.f32_unmasked && row_ok) {
+            if (!kNoLnOutputs && e.out_f32_t && !e.f32_unmasked && row_ok) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     if (n + j < e.n_store)
                         e.out_f32_t[(static_cast<long>(b) * e.n_store + n + j) * e.T + t] = x[j];
             }
-            if (e.out_f32 && row_ok) {
+            if (!kNoLnOutputs && e.out_f32 && row_ok) {
                 float4* o = reinterpret_cast<float4*>(e.out_f32 + row * e.ld_f32 + n);
                 o[0] = make_float4(x[0], x[1], x[2], x[3]);
                 o[1] = make_float4(x[4], x[5], x[6], x[7]);
             }
             float a[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) a[j] = e.act_tanh ? tanhf(x[j]) : lrelu(x[j], e.act_slope);
+            for (int j = 0; j < 8; ++j) a[j] = (!kNoLnOutputs && e.act_tanh) ? tanhf(x[j]) : lrelu(x[j], e.act_slope);
             o_act.q[g] = pack8(a);
         }
         if (dbg && c0 == 0) dbg[4] = clock64();
-        if (e.mrf_mode != MRF_NONE && e.mrf_mode != MRF_LAST) {
+        if (!kNoLnOutputs && e.mrf_mode != MRF_NONE && e.mrf_mode != MRF_LAST) {
             io.store(mrf_blk + c0, e.n_total, o_mrf);
         } else {
             if (e.out_raw) io.store(e.out_raw + row0 * e.ld_raw + n_base + c0, e.ld_raw, o_raw);
@@ -396,7 +401,7 @@ __device__ __forceinline__ void run_epilogue(const EpiParams& e, const Acc& acc,
         res_cur = res_nxt;
         mrf_cur = mrf_nxt;
     }
-    if (e.head_out && row_ok) e.head_out[row] = in_len ? head + e.head_b : 0.f;
+    if (kLnMode != 0 && e.head_out && row_ok) e.head_out[row] = in_len ? head + e.head_b : 0.f;
 }
 // ------------------------------------------------------------------------------------------------
 // Lean epilogue: the vocoder's hot subset only (bias, residual, row mask, MRF accumulate, raw and
