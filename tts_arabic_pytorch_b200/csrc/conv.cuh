@@ -42,6 +42,10 @@ struct ConvLayer {
     size_t smem_bytes2 = 0;
     // device data
     __half* w_packed = nullptr;  // [n_tiles][chunk][tap] tiles of n_tile x chunk_k, pre-swizzled
+    // 32 -> 32 channel layers only: the same weights as ceil(n_taps / 2) tiles of 32 x 64 (128-byte rows, 128-byte
+    // swizzle) holding taps (2g | 2g + 1) side by side along K, zeros beyond the last tap — conv_pair's conv2 when its
+    // TT panel stores [t | t + 1] per row (two taps per K = 64 group on the faster 128-byte operand rows)
+    __half* w_pair_packed = nullptr;
     float* bias = nullptr;       // [n_total] or null
     int n_tiles() const { return n_total / n_tile; }
 };
@@ -84,6 +88,7 @@ struct ConvPairPlan {
     int ok = 0;
     int C = 0, m_out = 0, h2 = 0, dil = 1, rows_panel = 0, tt_rows = 0;
     int x_slots = 0, tt_slots = 0, w2_resident = 0, b_stages = 0, tmem_cols = 0;
+    int tt_pair = 0;   // C = 32: TT rows hold [t | t + 1] (128 bytes), conv2 contracts two taps per K = 64 group (conv_pair.cu)
     size_t smem_bytes = 0;
     const __half* ident = nullptr;   // device: C x C identity in the packed weight-tile layout (shared per C, never freed)
 };

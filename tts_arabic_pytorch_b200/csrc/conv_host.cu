@@ -212,6 +212,21 @@ int conv_layer_create(ConvLayer& L, int cin_logical, int cin_stored, int n_total
             }
     TTSB_CHECK_CUDA(cudaMalloc(&L.w_packed, total * sizeof(__half)));
     TTSB_CHECK_CUDA(cudaMemcpy(L.w_packed, packed.data(), total * sizeof(__half), cudaMemcpyHostToDevice));
+    if (cin_stored == 32 && n_total == 32 && n_tile == 32 && cin_logical == 32) {
+        const int n_pairs = (n_taps + 1) / 2;
+        std::vector<__half> pp(static_cast<size_t>(n_pairs) * 32 * 64, __float2half(0.f));
+        for (int g = 0; g < n_pairs; ++g) {
+            uint8_t* tile = reinterpret_cast<uint8_t*>(pp.data() + static_cast<size_t>(g) * 32 * 64);
+            for (int n = 0; n < 32; ++n)
+                for (int kk = 0; kk < 64; ++kk) {
+                    const int tap = 2 * g + (kk >> 5);
+                    const float v = tap < n_taps ? w_logical[(static_cast<size_t>(n) * n_taps + tap) * cin_logical + (kk & 31)] : 0.f;
+                    *reinterpret_cast<__half*>(tile + wtile_offset(n, kk, 64)) = __float2half(v);
+                }
+        }
+        TTSB_CHECK_CUDA(cudaMalloc(&L.w_pair_packed, pp.size() * sizeof(__half)));
+        TTSB_CHECK_CUDA(cudaMemcpy(L.w_pair_packed, pp.data(), pp.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    }
     if (bias) {
         TTSB_CHECK_CUDA(cudaMalloc(&L.bias, n_total * sizeof(float)));
         TTSB_CHECK_CUDA(cudaMemcpy(L.bias, bias, n_total * sizeof(float), cudaMemcpyHostToDevice));
@@ -221,7 +236,9 @@ int conv_layer_create(ConvLayer& L, int cin_logical, int cin_stored, int n_total
 
 void conv_layer_destroy(ConvLayer& L) {
     if (L.w_packed) cudaFree(L.w_packed);
+    if (L.w_pair_packed) cudaFree(L.w_pair_packed);
     if (L.bias) cudaFree(L.bias);
+    L.w_pair_packed = nullptr;
     L.w_packed = nullptr;
     L.bias = nullptr;
 }

@@ -44,6 +44,9 @@ struct ConvPairArgs {
     int tt_rows;      // TT panel rows per chunk (multiple of 8, >= 128 + 2*h2)
     int x_slots, tt_slots;
     int w2_resident, b_stages;
+    int tt_pair;      // C = 32, resident W2: TT rows are 128 bytes [mid[t] | mid[t + 1]] and W2 comes as ceil(k / 2) tiles of
+                      // 32 x 64 (taps 2g | 2g + 1): two taps per K = 64 group on 128-byte-swizzled operand rows (42 instead of
+                      // 69 cycles per tcgen05.mma, profiles/r01_s21_mma_rate.txt); the mid epilogue writes every row twice
     int w2_x2;        // streamed W2 only: one pass of the W2 ring feeds conv2 of TWO consecutive items (both TT slots, both acc2 buffers)
     int smem_res;     // 1: kernel instantiated with kSmemRes (host-side record; see conv_pair_forward)
     int in_act;       // 1: x is stored activated (lrelu(x)): the TMA panel IS conv1's operand — no in-place transform, the conv1
@@ -118,17 +121,20 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     const int row_bytes = args.chunk_k * 2;
     const int panel_bytes = args.rows_panel * row_bytes;
     const int xslot_bytes = args.n_chunks * panel_bytes;
-    const int ttp_bytes = args.tt_rows * row_bytes;
+    const int tt_row_bytes = args.tt_pair ? 128 : row_bytes;
+    const int ttp_bytes = args.tt_rows * tt_row_bytes;
     const int ttslot_bytes = args.n_chunks * ttp_bytes;
     const int btile_bytes = C * row_bytes;
     const int n_btiles = args.n_chunks * args.n_taps;
+    const int b2tile_bytes = args.tt_pair ? C * 128 : btile_bytes;                  // W2 tiles (resident form)
+    const int n_b2tiles = args.tt_pair ? (args.n_taps + 1) / 2 : n_btiles;
     const int h1 = args.h2 * args.dil;
 
     uint8_t* smem_x = smem;
     uint8_t* smem_tt = smem_x + args.x_slots * xslot_bytes;
     uint8_t* smem_w1 = smem_tt + args.tt_slots * ttslot_bytes;
     uint8_t* smem_w2 = smem_w1 + n_btiles * btile_bytes;
-    uint8_t* smem_end = smem_w2 + (args.w2_resident ? n_btiles : args.b_stages) * btile_bytes;
+    uint8_t* smem_end = smem_w2 + (args.w2_resident ? n_b2tiles * b2tile_bytes : args.b_stages * btile_bytes);
     uint64_t* x_full = reinterpret_cast<uint64_t*>(smem_end);
     uint64_t* xl_full = x_full + kPairMaxX;
     uint64_t* x_empty = xl_full + kPairMaxX;
@@ -179,14 +185,14 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         // ---------------- TMA producer: resident weights once, then one x panel per item ----------------
         if (elect_one()) {
             const uint32_t wbytes = n_btiles * btile_bytes;
-            mbar_expect_tx(w_full, wbytes * (args.w2_resident ? 2 : 1));
+            mbar_expect_tx(w_full, wbytes + (args.w2_resident ? n_b2tiles * b2tile_bytes : 0));
             for (int i = 0; i < n_btiles; ++i)
                 bulk_load_1d(smem_w1 + i * btile_bytes, reinterpret_cast<const uint8_t*>(args.w1) + static_cast<size_t>(i) * btile_bytes,
                              btile_bytes, w_full);
             if (args.w2_resident)
-                for (int i = 0; i < n_btiles; ++i)
-                    bulk_load_1d(smem_w2 + i * btile_bytes, reinterpret_cast<const uint8_t*>(args.w2) + static_cast<size_t>(i) * btile_bytes,
-                                 btile_bytes, w_full);
+                for (int i = 0; i < n_b2tiles; ++i)
+                    bulk_load_1d(smem_w2 + i * b2tile_bytes, reinterpret_cast<const uint8_t*>(args.w2) + static_cast<size_t>(i) * b2tile_bytes,
+                                 b2tile_bytes, w_full);
             int sx = 0, it = 0;
             uint32_t px = 1;   // parity to wait on the EMPTY barrier (first lap passes)
             for (int idx = blockIdx.x; idx < args.n_work; idx += grid, ++it) {
@@ -321,6 +327,41 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         if (two) tlp_mark(args, it + 1, 6);
                         ptt ^= two ? 3u : 1u;
                     }
+                } else if (args.tt_pair) {
+                    // two taps per K = 64 group: A rows are [mid[t] | mid[t + 1]] (128-byte swizzle), group g reads the
+                    // panel shifted by 2g rows against W2's pair tile g; the last (odd) tap uses the first half only
+                    const uint64_t desc_hi2 = (static_cast<uint64_t>(((8u * 128u) >> 4) | (1u << 14) | (2u << 29)) << 32) | (1u << 16);
+                    const uint32_t b2tile_u = static_cast<uint32_t>(b2tile_bytes) >> 4;
+                    for (int idx = blockIdx.x; idx < args.n_work; idx += grid, ++it) {
+                        mbar_wait(&tt_full[st], (ptt >> st) & 1u, args.err_flag, 306);
+                        mbar_wait(&acc2_empty[b2], (pe2 >> b2) & 1u, args.err_flag, 307);
+                        pe2 ^= 1u << b2;
+                        tc_fence_after();
+                        tlp_mark(args, it, 5);
+                        const uint32_t d = tmem_base + acc2_col + b2 * C;
+                        uint32_t a_lo = tt_lo0 + st * ttslot_u;
+                        uint32_t b_lo = w2_lo0;
+                        uint32_t accumulate = 0;
+                        for (int g = 0; g < n_b2tiles; ++g) {
+                            const int nk = (2 * g + 1 < args.n_taps) ? 4 : 2;
+                            if (!(args.debug & 8)) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    if (k < nk)
+                                        umma_f16(d, desc_hi2 | ((a_lo + 2 * k) & 0x3FFFu), desc_hi2 | ((b_lo + 2 * k) & 0x3FFFu), idesc,
+                                                 accumulate | static_cast<uint32_t>(k));
+                            }
+                            accumulate = 1;
+                            a_lo += 16;            // two rows of 128 bytes
+                            b_lo += b2tile_u;
+                        }
+                        umma_commit(&tt_empty[st]);
+                        umma_commit(&acc2_full[b2]);
+                        tlp_mark(args, it, 6);
+                        ptt ^= 1u << st;
+                        if (args.tt_slots == 2) st ^= 1;
+                        b2 ^= 1;
+                    }
                 } else
                 for (int idx = blockIdx.x; idx < args.n_work; idx += grid, ++it) {
                     mbar_wait(&tt_full[st], (ptt >> st) & 1u, args.err_flag, 306);
@@ -436,7 +477,13 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         const float y = v[ci & 1][g * 8 + j] + bs[j];
                         a[j] = valid ? fmaxf(y, y * slope) : 0.f;      // slope in (0, 1): max(y, slope * y) == lrelu(y)
                     }
-                    if (!(args.debug & 2)) sts128(tt_base + chunk * ttp_bytes + ((u0 + g) ^ phase) * 16, pack8(a));
+                    if (args.tt_pair) {
+                        // row m, first half, and row m - 1, second half (128-byte rows, unit ^= row & 7)
+                        const uint4 pk = pack8(a);
+                        const uint32_t ra = tt_base - m * row_bytes + m * 128;      // this row; the slot is 1 KB aligned
+                        sts128(ra + ((static_cast<uint32_t>(g) ^ ((ra >> 7) & 7u)) << 4), pk);
+                        if (m > 0) sts128(ra - 128 + ((static_cast<uint32_t>(4 + g) ^ (((ra - 128) >> 7) & 7u)) << 4), pk);
+                    } else if (!(args.debug & 2)) sts128(tt_base + chunk * ttp_bytes + ((u0 + g) ^ phase) * 16, pack8(a));
                 }
             }
             if (m == 0) tlp_mark(args, it, 14);
@@ -566,19 +613,27 @@ ConvPairPlan conv_pair_plan(const ConvLayer& L1, const ConvLayer& L2) {
     p.C = C; p.h2 = h2; p.dil = dil;
     p.m_out = kTileM - 2 * h2;
     if (p.m_out < 64) return p;
-    p.rows_panel = round_up(kTileM + 2 * h2 * dil, 8);
+    // C = 32: TT rows of 128 bytes holding [t | t + 1], W2 as pair tiles (see ConvPairArgs::tt_pair). The 128-byte swizzle
+    // wants every panel and tile 1 KB aligned: the x slots (64-byte rows) are padded to a multiple of 16 rows.
+    static const int want_tt_pair = getenv("TTSB_PAIR_TT2") ? atoi(getenv("TTSB_PAIR_TT2")) : 1;
+    // k = 3 pairs are bound by the epilogue groups, not by the MMAs: there the second store per row costs more than the
+    // cheaper MMAs give back (129 -> 141 us per 16 utterances); k = 7 / 11: 197 -> 156 / 274 -> 170 us (profiles/r02_s27_...)
+    const bool tt_pair = want_tt_pair >= 2 ? (C == 32 && L2.w_pair_packed != nullptr && k >= 3)
+                                           : (want_tt_pair && C == 32 && L2.w_pair_packed != nullptr && k >= 5);
+    p.rows_panel = round_up(kTileM + 2 * h2 * dil, tt_pair ? 16 : 8);
     p.tt_rows = round_up(kTileM + 2 * h2, 8);
     if (p.rows_panel > 256) return p;
     const size_t row_bytes = L1.chunk_k * 2;
     const size_t xslot = static_cast<size_t>(L1.n_chunks) * p.rows_panel * row_bytes;
-    const size_t ttslot = static_cast<size_t>(L1.n_chunks) * p.tt_rows * row_bytes;
+    const size_t ttslot = static_cast<size_t>(L1.n_chunks) * p.tt_rows * (tt_pair ? 128 : row_bytes);
     const size_t btile = static_cast<size_t>(C) * row_bytes;
     const size_t w1 = static_cast<size_t>(L1.n_chunks) * k * btile;
+    const size_t w2_res = tt_pair ? static_cast<size_t>((k + 1) / 2) * C * 128 : w1;
     const size_t avail = kPairSmemMax - kPairFixed;
     static const int force_stream = getenv("TTSB_PAIR_STREAM") ? atoi(getenv("TTSB_PAIR_STREAM")) : 0;
-    for (int res = force_stream ? 0 : 1; res >= 0 && !p.ok; --res) {
+    for (int res = (force_stream && !tt_pair) ? 0 : 1; res >= (tt_pair ? 1 : 0) && !p.ok; --res) {
         const int min_b = std::min<int>(4, L1.n_chunks * k);
-        const size_t wbytes = w1 + (res ? w1 : min_b * btile);
+        const size_t wbytes = w1 + (res ? w2_res : min_b * btile);
         if (wbytes + 2 * xslot + ttslot > avail) continue;
         const size_t rem = avail - wbytes;
         p.tt_slots = rem >= 2 * ttslot + 2 * xslot ? 2 : 1;
@@ -590,7 +645,8 @@ ConvPairPlan conv_pair_plan(const ConvLayer& L1, const ConvLayer& L2) {
             p.b_stages = static_cast<int>(std::min<size_t>(kPairMaxB, min_b + left / btile));
             p.b_stages = std::min(p.b_stages, L1.n_chunks * k);
         }
-        p.smem_bytes = kPairFixed + p.x_slots * xslot + p.tt_slots * ttslot + w1 + (res ? w1 : p.b_stages * btile);
+        p.smem_bytes = kPairFixed + p.x_slots * xslot + p.tt_slots * ttslot + w1 + (res ? w2_res : p.b_stages * btile);
+        p.tt_pair = (res && tt_pair) ? 1 : 0;
         p.ok = 1;
     }
     p.tmem_cols = 32;
@@ -648,7 +704,8 @@ int conv_pair_forward(const ConvLayer& L1, const ConvLayer& L2, const ConvPairPl
     static const int want_w2_x2 = getenv("TTSB_PAIR_W2X2") ? atoi(getenv("TTSB_PAIR_W2X2")) : 1;
     a.w2_x2 = (want_w2_x2 && !plan.w2_resident && plan.tt_slots == 2) ? 1 : 0;
     a.in_act = in_act ? 1 : 0;
-    a.w1 = L1.w_packed; a.w2 = L2.w_packed;
+    a.tt_pair = plan.tt_pair;
+    a.w1 = L1.w_packed; a.w2 = plan.tt_pair ? L2.w_pair_packed : L2.w_packed;
     a.bias1 = L1.bias;
     a.slope = slope;
     a.err_flag = rt.err_flag;
