@@ -109,7 +109,7 @@ __device__ __forceinline__ void pair_transform_slot(const ConvPairArgs& args, ui
 
 // kSmemRes: the final epilogue takes its residual rows from the x panel in shared memory (activated chain, deep x ring;
 // see run_epilogue_lean) and releases the panel itself: x_empty then counts conv1's commit + the 4 final-epilogue warps.
-template <int kTmemCols, int kEpi, bool kSmemRes>
+template <int kTmemCols, int kEpi, bool kSmemRes, bool kTtPair>
 __global__ void __launch_bounds__(kPairThreads, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ ConvPairArgs args) {
     constexpr int kKSteps = kTmemCols == 128 ? 2 : 4;
@@ -118,16 +118,19 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     uint8_t* smem = smem_raw + ((1024u - (raw_u32 & 1023u)) & 1023u);
 
     const int C = args.C;
+    // a template parameter, not args.tt_pair: a run-time flag in the mid epilogue's store loop cost the C = 64
+    // instantiations 5-15 % (round-2 session 28)
+    constexpr bool tt_pair = kTtPair;
     const int row_bytes = args.chunk_k * 2;
     const int panel_bytes = args.rows_panel * row_bytes;
     const int xslot_bytes = args.n_chunks * panel_bytes;
-    const int tt_row_bytes = args.tt_pair ? 128 : row_bytes;
+    const int tt_row_bytes = tt_pair ? 128 : row_bytes;
     const int ttp_bytes = args.tt_rows * tt_row_bytes;
     const int ttslot_bytes = args.n_chunks * ttp_bytes;
     const int btile_bytes = C * row_bytes;
     const int n_btiles = args.n_chunks * args.n_taps;
-    const int b2tile_bytes = args.tt_pair ? C * 128 : btile_bytes;                  // W2 tiles (resident form)
-    const int n_b2tiles = args.tt_pair ? (args.n_taps + 1) / 2 : n_btiles;
+    const int b2tile_bytes = tt_pair ? C * 128 : btile_bytes;                  // W2 tiles (resident form)
+    const int n_b2tiles = tt_pair ? (args.n_taps + 1) / 2 : n_btiles;
     const int h1 = args.h2 * args.dil;
 
     uint8_t* smem_x = smem;
@@ -327,7 +330,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         if (two) tlp_mark(args, it + 1, 6);
                         ptt ^= two ? 3u : 1u;
                     }
-                } else if (args.tt_pair) {
+                } else if (tt_pair) {
                     // two taps per K = 64 group: A rows are [mid[t] | mid[t + 1]] (128-byte swizzle), group g reads the
                     // panel shifted by 2g rows against W2's pair tile g; the last (odd) tap uses the first half only
                     const uint64_t desc_hi2 = (static_cast<uint64_t>(((8u * 128u) >> 4) | (1u << 14) | (2u << 29)) << 32) | (1u << 16);
@@ -477,7 +480,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         const float y = v[ci & 1][g * 8 + j] + bs[j];
                         a[j] = valid ? fmaxf(y, y * slope) : 0.f;      // slope in (0, 1): max(y, slope * y) == lrelu(y)
                     }
-                    if (args.tt_pair) {
+                    if (tt_pair) {
                         // row m, first half, and row m - 1, second half (128-byte rows, unit ^= row & 7)
                         const uint4 pk = pack8(a);
                         const uint32_t ra = tt_base - m * row_bytes + m * 128;      // this row; the slot is 1 KB aligned
@@ -654,18 +657,26 @@ ConvPairPlan conv_pair_plan(const ConvLayer& L1, const ConvLayer& L2) {
     return p;
 }
 
-template <int kCols, int kEpi, bool kSmemRes>
-static int launch_pair_impl(const CUtensorMap& tm, const ConvPairArgs& a, int grid, size_t smem, cudaStream_t s) {
+template <int kCols, int kEpi, bool kSmemRes, bool kTtPair>
+static int launch_pair_impl2(const CUtensorMap& tm, const ConvPairArgs& a, int grid, size_t smem, cudaStream_t s) {
     static PerDeviceOnce configured;
     if (!configured.here()) {
-        TTSB_CHECK_CUDA(cudaFuncSetAttribute(conv_pair_kernel<kCols, kEpi, kSmemRes>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        TTSB_CHECK_CUDA(cudaFuncSetAttribute(conv_pair_kernel<kCols, kEpi, kSmemRes, kTtPair>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(kPairSmemMax)));
         configured.here() = true;
     }
-    conv_pair_kernel<kCols, kEpi, kSmemRes><<<grid, kPairThreads, smem, s>>>(tm, a);
+    conv_pair_kernel<kCols, kEpi, kSmemRes, kTtPair><<<grid, kPairThreads, smem, s>>>(tm, a);
     count_launch();
     TTSB_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+template <int kCols, int kEpi, bool kSmemRes>
+static int launch_pair_impl(const CUtensorMap& tm, const ConvPairArgs& a, int grid, size_t smem, cudaStream_t s) {
+    if constexpr (kCols == 128) {
+        if (a.tt_pair) return launch_pair_impl2<kCols, kEpi, kSmemRes, true>(tm, a, grid, smem, s);
+    }
+    return launch_pair_impl2<kCols, kEpi, kSmemRes, false>(tm, a, grid, smem, s);
 }
 
 // kEpi: 1 lean, 2 lean + MRF accumulate, 3 lean with ONE activated output and nothing else (the activated chain's pairs 0 / 1)
