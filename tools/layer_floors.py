@@ -74,21 +74,28 @@ def generator_layers(frames):
                     out.append(layer('s%d C%d k%d d1 conv2' % (s, c, k), rows, c, c, k,
                                      extra_rw=rows * c * 2 * (1 if ACT_CHAIN else 2) + mrf))
                 else:
-                    out.append(layer('s%d C%d k%d d%d pair' % (s, c, k, d), rows, c, c, k, extra_rw=mrf,
-                                     resident=True, fused=2))
+                    pair = layer('s%d C%d k%d d%d pair' % (s, c, k, d), rows, c, c, k, extra_rw=mrf, resident=True, fused=2)
+                    if c == 32 and k >= 5 and TT_PAIR:
+                        # conv2 contracts two taps per K = 64 group on 128-byte rows (conv_pair.cu, tt_pair): the same
+                        # number of instructions at 42 instead of 69 cycles
+                        n_each = rows / 128.0 * k * 2
+                        pair['mma'] = n_each * (MMA_CYC_SW64[32] + MMA_CYC_SW128[32]) / (SMS * CLK)
+                    out.append(pair)
     out.append(dict(name='conv_post 32->1 k7 + tanh', flops=2.0 * frames * 256 * 32 * 7, mma=0.0, wbytes=0.0,
                     hbm=frames * 256 * (32 * 2 + 4) / HBM))
     return out
 
 
 ACT_CHAIN = True     # round-2 data flow; pass a third argument `r1` for round-1 launch lists
+TT_PAIR = True       # round-2 C = 32 conv2 (see generator_layers); off with `r1`
 
 
 def main():
-    global ACT_CHAIN
+    global ACT_CHAIN, TT_PAIR
     path, frames = sys.argv[1], int(sys.argv[2])
     if len(sys.argv) > 3 and sys.argv[3] == 'r1':
         ACT_CHAIN = False
+        TT_PAIR = False
     rows = [r for r in csv.reader(l for l in open(path) if l.startswith('"'))][1:]
     durs = [(re.sub(r'\(.*', '', r[4]).replace('void ttsb::', '').replace('ttsb::', ''),
              float(r[-1].replace(',', '')) * 1e-9) for r in rows]
