@@ -21,7 +21,8 @@ def _run(tmp_path, name, env_extra):
         pytest.fail('GPU tests need a CUDA device')
     out = os.path.join(str(tmp_path), name + '.npz')
     env = dict(os.environ)
-    for k in ('TTSB_PAIR', 'TTSB_TMA_OUT', 'TTSB_ATTENTION', 'TTSB_CLUSTER', 'TTSB_PAIR_SMEM_RES', 'TTSB_ACT_CHAIN'):
+    for k in ('TTSB_PAIR', 'TTSB_TMA_OUT', 'TTSB_ATTENTION', 'TTSB_CLUSTER', 'TTSB_PAIR_SMEM_RES', 'TTSB_ACT_CHAIN', 'TTSB_EPI_ACT',
+              'TTSB_EPI_TMA_IN', 'TTSB_EPI_RING', 'TTSB_PAIR_TT2', 'TTSB_PAIR_W2X2', 'TTSB_PAIR_ACT_ONLY', 'TTSB_OCC2'):
         env.pop(k, None)
     env.update(env_extra)
     r = subprocess.run([sys.executable, HELPER, out], env=env, capture_output=True, text=True, timeout=600)
@@ -69,3 +70,19 @@ def test_weight_multicast_and_transform_placement_do_not_change_results(default_
     assert np.array_equal(default_run['wav'], b['wav'])
     c = _run(tmp_path, 'rawchain', {'TTSB_ACT_CHAIN': '0'})           # round-1 data flow: raw + activated copies
     assert _rel_rms(default_run['wav'], c['wav']) < tol.WAV_REL_RMS
+
+
+def test_round2_epilogue_and_pair_forms_are_bit_exact(default_run, tmp_path):
+    """The round-2 kernel forms change schedules and data movement, not arithmetic: the act-only and TMA-in epilogues of
+    conv_tc2 against the round-1 lean epilogue, a single look-ahead slot against two, conv_pair's two-taps-per-row conv2
+    (same K = 16 steps in the same order), two items per W2 ring pass and the act-only final epilogue — every one must
+    reproduce the default run's mel and waveform exactly."""
+    for name, env in (('lean_epilogues', {'TTSB_EPI_ACT': '0', 'TTSB_EPI_TMA_IN': '0'}),
+                      ('ring1', {'TTSB_EPI_RING': '1'}),
+                      ('tt64', {'TTSB_PAIR_TT2': '0'}),
+                      ('tt128_all_k', {'TTSB_PAIR_TT2': '2'}),
+                      ('w2_one_item', {'TTSB_PAIR_W2X2': '0'}),
+                      ('pair_lean_final', {'TTSB_PAIR_ACT_ONLY': '0'})):
+        other = _run(tmp_path, name, env)
+        assert np.array_equal(default_run['mel'], other['mel']), name
+        assert np.array_equal(default_run['wav'], other['wav']), name

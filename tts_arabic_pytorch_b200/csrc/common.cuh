@@ -209,7 +209,11 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag, int code) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
+#ifdef TTSB_MBAR_SPIN   // experiment: default try_wait time limit (tools/build_flags.py)
+    while (!mbar_try_wait(bar, parity)) {
+#else
     while (!mbar_try_wait_hint(bar, parity, 100000u)) {
+#endif
         if (clock64() - t0 > 6000000000ll) {
             if (err_flag) atomicExch(err_flag, code);
             __trap();
