@@ -197,7 +197,8 @@ class FastPitch2Wave(nn.Module):
     # ------------------------------------------------------------------ ids -> waveforms (batch core)
     @torch.inference_mode()
     def synthesize_ids(self, id_list: List[torch.Tensor], speed=1., speaker_id=0, denoise=0., pitch_transform=None,
-                       max_duration=75, to_cpu=True, pad_to: int = 0, frame_len_hook=None, return_padded=False):
+                       max_duration=75, to_cpu=True, pad_to: int = 0, frame_len_hook=None, return_padded=False,
+                       host_alloc=None):
         """Core used by every tts_* method: padded FastPitch batch -> ONE masked vocoder call ->
         (optional) batched denoiser -> single D2H copy. Returns (list of 1-D waveforms in input order,
         list of [80,T_i] mels)."""
@@ -205,13 +206,20 @@ class FastPitch2Wave(nn.Module):
             id_list, speed, speaker_id, pitch_transform, None, None, None, max_duration, channel_last=True,
             pad_to=pad_to, frame_len_hook=frame_len_hook)
         host = None
-        if to_cpu and not return_padded and denoise <= 0:
+        n_cols = mel_cl.shape[1] * self.vocoder.hop
+        if host_alloc is not None:
+            # parallel.synthesize (host_shm): this rank's rows of the shared pinned segment, sorted-batch order
+            host = host_alloc(mel_cl.shape[0], n_cols)
+        elif to_cpu and not return_padded:
             # the waveforms' pinned destination is known up front: finished groups of utterances leave over PCIe while
             # the generator works on the next group (Generator.run, host_out)
-            host = torch.empty(mel_cl.shape[0], mel_cl.shape[1] * self.vocoder.hop, dtype=torch.float32, pin_memory=True)
-        wav = self.vocoder.run(mel_cl=mel_cl, lens=dec_lens, host_out=host)              # [B, T_max*hop]
+            host = torch.empty(mel_cl.shape[0], n_cols, dtype=torch.float32, pin_memory=True)
+        wav = self.vocoder.run(mel_cl=mel_cl, lens=dec_lens, host_out=host if denoise <= 0 else None)   # [B, T_max*hop]
         if denoise > 0:
             wav = self.denoiser.denoise_batch(wav, dec_lens * self.vocoder.hop, denoise)
+            if host is not None:              # the generator's output was not the final waveform: one copy of the result
+                host.copy_(wav, non_blocking=True)
+                torch.cuda.current_stream(wav.device).synchronize()
         if return_padded:
             # device-resident form for parallel.synthesize: padded waveforms in SORTED order + what undoes the sort
             return wav, dec_lens * self.vocoder.hop, inverse, mel

@@ -65,6 +65,7 @@ class HostSharedBuffer:
             except Exception:
                 pass
         import numpy as np
+        self.rows, self.cols = rows, cols
         self.array = np.ndarray((rows, cols), dtype=np.float32, buffer=self.shm.buf)
         self.tensor = torch.from_numpy(self.array)
         self.registered = False
@@ -85,6 +86,108 @@ class HostSharedBuffer:
                 self.shm.unlink()
         except Exception:
             pass
+
+
+# Persistent delivery segments. Creating a shared segment and page-locking it (cudaHostRegister) in every rank costs
+# hundreds of milliseconds per GiB — several times the synthesis itself when done per call (measured: 438 ms per step at
+# N = 2 against 122 ms of compute). Two segments per (group, destination) are kept and used alternately, grown on demand:
+# the waveforms a call returns are VIEWS of one of them and stay valid until the call after next (clone to keep longer).
+_SHM_POOL = {}
+
+
+def _shm_segment(rank: int, dst: int, group, n_floats: int, dev) -> HostSharedBuffer:
+    """Collective over `group`: every rank passes the same size and makes the same reuse / regrow decision. The segment is
+    used as a flat fp32 array (`.tensor[0]`); rank r's rows are a CONTIGUOUS [B_r, cols_r] block of it, so the device ->
+    host copies are plain contiguous transfers."""
+    key = (id(group) if group is not None else 0, dst)
+    pool = _SHM_POOL.setdefault(key, {'bufs': [None, None], 'turn': 0})
+    turn = pool['turn']
+    pool['turn'] ^= 1
+    buf = pool['bufs'][turn]
+    if buf is not None and buf.cols >= n_floats:
+        return buf
+    if buf is not None:
+        dist.barrier(group=group)            # nobody still copies into the old segment
+        buf.close()
+    cap = max(1, -(-n_floats // (1 << 20)) * (1 << 20))
+    name_t = torch.zeros(1, dtype=torch.int64, device=dev)
+    if rank == dst:
+        import os
+        name_t[0] = int.from_bytes(os.urandom(6), 'little')
+    dist.broadcast(name_t, src=dst, group=group)
+    name = 'ttsb_%x' % int(name_t[0])
+    buf = HostSharedBuffer(name, 1, cap, create=True) if rank == dst else None
+    dist.barrier(group=group)                # the segment exists
+    if rank != dst:
+        buf = HostSharedBuffer(name, 1, cap, create=False)
+    pool['bufs'][turn] = buf
+    return buf
+
+
+def _close_shm_pool():
+    for pool in _SHM_POOL.values():
+        for b in pool['bufs']:
+            if b is not None:
+                b.close()
+    _SHM_POOL.clear()
+
+
+import atexit  # noqa: E402
+atexit.register(_close_shm_pool)
+
+
+def _synthesize_host_shm(model, id_list, shards, pad_to, rank, world, dst, group, frame_len_hook, speed, speaker_id, denoise,
+                         pitch_transform, max_duration, return_stats):
+    """deliver = 'host_shm': every rank's generator writes its finished utterance groups straight into its rows of the
+    shared pinned segment (device -> host copies under the next group's compute, each over the rank's own PCIe link);
+    `dst` then only needs every rank's sample counts and sort permutation (two small all_gathers, which also order the
+    copies before the read) to hand out views in input order."""
+    dev = model.device
+    mine = shards[rank]
+    state = {}
+
+    def host_alloc(b_local: int, n_cols: int):
+        meta = torch.tensor([b_local, n_cols], dtype=torch.int64, device=dev)
+        metas = [torch.empty_like(meta) for _ in range(world)]
+        dist.all_gather(metas, meta, group=group)
+        rows_of = [int(m[0]) for m in metas]
+        cols_of = [int(m[1]) for m in metas]
+        sizes = [r * c for r, c in zip(rows_of, cols_of)]
+        buf = _shm_segment(rank, dst, group, sum(sizes), dev)
+        off = sum(sizes[:rank])
+        state.update(buf=buf, rows_of=rows_of, cols_of=cols_of, sizes=sizes)
+        return buf.tensor[0, off:off + b_local * n_cols].view(b_local, n_cols) if b_local else None
+
+    if mine:
+        wav, n_samples, inverse, _ = model.synthesize_ids([id_list[i] for i in mine], speed, speaker_id, denoise,
+                                                          pitch_transform, max_duration, to_cpu=False,
+                                                          pad_to=pad_to[rank], frame_len_hook=frame_len_hook,
+                                                          return_padded=True, host_alloc=host_alloc)
+        info = torch.stack([n_samples.to(dev), inverse.to(dev)], dim=1).contiguous()     # [B_local, 2], sorted-row order
+    else:
+        frame_len_hook(0)                     # keep the collectives matched
+        host_alloc(0, 1)
+        n_samples = torch.zeros(0, dtype=torch.int64, device=dev)
+        info = torch.zeros(0, 2, dtype=torch.int64, device=dev)
+    stats = {'frames': int(n_samples.sum()) // max(1, model.vocoder.hop), 'utterances': len(mine)}
+    rows_of = state['rows_of']
+    infos = [torch.empty(r * 2, dtype=torch.int64, device=dev) for r in rows_of]
+    if len(set(rows_of)) == 1:
+        dist.all_gather(infos, info.reshape(-1), group=group)
+    else:
+        _all_gather_ragged(infos, info.reshape(-1), group)
+    res = None
+    if rank == dst:
+        buf = state['buf']
+        per_rank, at = [], 0
+        for r in range(world):
+            inf = infos[r].reshape(-1, 2).tolist()
+            block = buf.tensor[0, at:at + state['sizes'][r]].view(rows_of[r], max(1, state['cols_of'][r])) if rows_of[r] else None
+            # shard position j of rank r sits in sorted row inverse[j]
+            per_rank.append([block[int(inf[j][1]), :int(inf[int(inf[j][1])][0])] for j in range(rows_of[r])])
+            at += state['sizes'][r]
+        res = unshard(per_rank, shards)
+    return (res, stats) if return_stats else res
 
 
 @torch.inference_mode()
@@ -116,6 +219,9 @@ def synthesize(model, id_list: List[torch.Tensor], speed=1., speaker_id=0, denoi
         wavs, _ = model.synthesize_ids(id_list, speed, speaker_id, denoise, pitch_transform, max_duration, to_cpu=True)
         stats = {'frames': sum(int(w.numel()) for w in wavs) // max(1, model.vocoder.hop), 'utterances': len(wavs)}
         return (wavs, stats) if return_stats else wavs
+    if world > 1 and deliver == 'host_shm':
+        return _synthesize_host_shm(model, id_list, shards, pad_to, rank, world, dst, group, frame_len_hook, speed, speaker_id,
+                                    denoise, pitch_transform, max_duration, return_stats)
     if mine:
         wav, n_samples, inverse, _ = model.synthesize_ids([id_list[i] for i in mine], speed, speaker_id, denoise,
                                                           pitch_transform, max_duration, to_cpu=False,
@@ -140,42 +246,6 @@ def synthesize(model, id_list: List[torch.Tensor], speed=1., speaker_id=0, denoi
             wav = host
         out = [wav[k, :int(n)] for k, n in enumerate(n_samples.tolist())]
         res = unshard([out], shards)
-        return (res, stats) if return_stats else res
-
-    if deliver == 'host_shm':
-        meta = torch.tensor([wav.shape[0], wav.shape[1]], dtype=torch.int64, device=dev)
-        metas = [torch.empty_like(meta) for _ in range(world)]
-        dist.all_gather(metas, meta, group=group)
-        rows_of = [int(m[0]) for m in metas]
-        n_max = max(int(m[1]) for m in metas)
-        total = sum(rows_of)
-        name_t = torch.zeros(1, dtype=torch.int64, device=dev)
-        if rank == dst:
-            import os
-            name_t[0] = int.from_bytes(os.urandom(6), 'little')
-        dist.broadcast(name_t, src=dst, group=group)
-        name = 'ttsb_%x' % int(name_t[0])
-        buf = HostSharedBuffer(name, total, n_max, create=True) if rank == dst else None
-        cnt_all = [torch.empty(r, dtype=torch.int64, device=dev) for r in rows_of]
-        dist.all_gather(cnt_all, n_samples, group=group) if len(set(rows_of)) == 1 else _all_gather_ragged(cnt_all, n_samples, group)
-        dist.barrier(group=group)             # the segment exists
-        if rank != dst:
-            buf = HostSharedBuffer(name, total, n_max, create=False)
-        r0 = sum(rows_of[:rank])
-        if wav.shape[0]:
-            buf.tensor[r0:r0 + wav.shape[0], :wav.shape[1]].copy_(wav, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
-        dist.barrier(group=group)             # every rank's rows are in host memory
-        res = None
-        if rank == dst:
-            per_rank, at = [], 0
-            for r in range(world):
-                cnt = cnt_all[r].tolist()
-                per_rank.append([buf.tensor[at + k, :int(n)].clone() for k, n in enumerate(cnt)])
-                at += rows_of[r]
-            res = unshard(per_rank, shards)
-        dist.barrier(group=group)
-        buf.close()
         return (res, stats) if return_stats else res
 
     got = gather_waveforms(wav, n_samples, dst=dst, group=group)

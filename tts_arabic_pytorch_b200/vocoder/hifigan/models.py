@@ -178,7 +178,7 @@ class Generator(nn.Module):
             ws = self._ws.get(nbytes, device)
             group = B
             if host_out is not None:
-                assert host_out.shape == wav.shape and host_out.dtype == torch.float32 and host_out.is_pinned()
+                assert host_out.shape == wav.shape and host_out.dtype == torch.float32 and host_out.device.type == 'cpu'
                 group = max(1, min(B, int(os.environ.get('TTSB_D2H_GROUP_FRAMES', '32768')) // max(T, 1)))
             if group >= B and host_out is None:
                 _lib.check(lib.ttsb_hifigan_forward(handle, _lib.ptr(mel_f32), _lib.ptr(mel_cl), _lib.ptr(lens), h_lens, B, T,
