@@ -246,10 +246,13 @@ __global__ void __launch_bounds__(256) t2_lstm_cell_kernel(const float* __restri
 __device__ __forceinline__ void t2_attention_body(float* sm, int b, const float* __restrict__ ah,
                                                   const float* __restrict__ memory, const float* __restrict__ pmem,
                                                   const int* __restrict__ lens, const __half* __restrict__ wq,
-                                                  const float* __restrict__ wloc_conv, const float* __restrict__ wloc_dense,
-                                                  const float* __restrict__ v, float* __restrict__ aw, float* __restrict__ awc,
+                                                  const float* wloc_conv, const float* wloc_dense,
+                                                  const float* v, float* __restrict__ aw, float* __restrict__ awc,
                                                   float* __restrict__ ctx, float* __restrict__ align_out, int L, int H, int M,
-                                                  int A, int NF, int KL) {
+                                                  int A, int NF, int KL, const float* __restrict__ q_in = nullptr,
+                                                  const float* att_tables = nullptr) {
+    // q_in (persistent decoder): the query projection W_q . ah[b] was computed by ALL CTAs in the phase before (one dot
+    // product per warp instead of A / nwarp sequential L2 round trips here); same warp_dot_h, same values
     float* q = sm;                 // [A]
     float* w_prev = q + A;         // [L + KL - 1] padded previous weights
     float* w_cum = w_prev + L + KL; // [L + KL - 1]
@@ -258,14 +261,29 @@ __device__ __forceinline__ void t2_attention_body(float* sm, int b, const float*
     const int len = lens[b];
     const int pad = (KL - 1) / 2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    // processed memory of THIS utterance [L, A]; att_tables (persistent decoder): shared-memory copies of
+    // [location conv | location dense | v | this utterance's processed memory], staged once per launch — read through
+    // global memory these small tables were evicted from L1 by every LSTM phase, and the energy loop is a chain of
+    // dependent loads (31 taps, then 32 filters per output): ~50 k cycles per step of L2 latency (tools/t2_phases.py)
+    const float* pmem_b = pmem + static_cast<size_t>(b) * L * A;
+    if (att_tables != nullptr) {
+        wloc_conv = att_tables;
+        wloc_dense = att_tables + 2 * KL * NF;
+        v = wloc_dense + NF * A;
+        pmem_b = v + A;
+    }
     // the query rows all multiply the same attention-LSTM output: stage it once (it was written by other CTAs: ld.cg)
     float* ahs = sm + ((A + 2 * (L + KL) + L + 32 + 3) & ~3);   // [H], 16-byte aligned for the float4 accesses
-    for (int k = threadIdx.x * 4; k < H; k += blockDim.x * 4)
-        *reinterpret_cast<float4*>(ahs + k) = ld_state4(ah + static_cast<size_t>(b) * H + k);
-    __syncthreads();
-    for (int a = warp; a < A; a += nwarp) {
-        const float d = warp_dot_h(wq + static_cast<size_t>(a) * H, ahs, H, lane);
-        if (lane == 0) q[a] = d;
+    if (q_in != nullptr) {
+        for (int a = threadIdx.x; a < A; a += blockDim.x) q[a] = __ldcg(q_in + static_cast<size_t>(b) * A + a);
+    } else {
+        for (int k = threadIdx.x * 4; k < H; k += blockDim.x * 4)
+            *reinterpret_cast<float4*>(ahs + k) = ld_state4(ah + static_cast<size_t>(b) * H + k);
+        __syncthreads();
+        for (int a = warp; a < A; a += nwarp) {
+            const float d = warp_dot_h(wq + static_cast<size_t>(a) * H, ahs, H, lane);
+            if (lane == 0) q[a] = d;
+        }
     }
     for (int i = threadIdx.x; i < L + KL - 1; i += blockDim.x) {
         const int l = i - pad;
@@ -273,7 +291,47 @@ __device__ __forceinline__ void t2_attention_body(float* sm, int b, const float*
         w_cum[i] = (l >= 0 && l < L) ? awc[b * L + l] : 0.f;
     }
     __syncthreads();
-    // energies: one warp per position
+    // energies. Persistent decoder with the tables in shared memory (NF = 32 filters, A = 128): a warp works on FOUR
+    // positions at once — the 31-tap location conv and the 32-filter dense sum are chains of dependent multiply-adds (one
+    // shared-memory load + one shuffle per link), and one position at a time left the warp waiting on every link (~10 k
+    // cycles per position: tools/t2_phases.py). Every (position, a) chain keeps the order of the loop below: same values.
+    if (att_tables != nullptr && NF == 32 && A == 128) {
+        for (int l0 = warp; l0 < L; l0 += 4 * nwarp) {
+            int lp[4];
+            float f[4], sacc[4][4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) { lp[p] = min(l0 + p * nwarp, L - 1); f[p] = 0.f; }
+            for (int k = 0; k < KL; ++k) {
+                const float c0 = wloc_conv[k * NF + lane], c1 = wloc_conv[(KL + k) * NF + lane];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) f[p] += c0 * w_prev[lp[p] + k] + c1 * w_cum[lp[p] + k];
+            }
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                for (int ai = 0; ai < 4; ++ai) sacc[p][ai] = q[lane + 32 * ai] + pmem_b[static_cast<size_t>(lp[p]) * A + lane + 32 * ai];
+            for (int nf = 0; nf < 32; ++nf) {
+                float wd[4], fv[4];
+#pragma unroll
+                for (int ai = 0; ai < 4; ++ai) wd[ai] = wloc_dense[nf * A + lane + 32 * ai];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) fv[p] = __shfl_sync(0xffffffffu, f[p], nf);
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+#pragma unroll
+                    for (int ai = 0; ai < 4; ++ai) sacc[p][ai] += wd[ai] * fv[p];
+            }
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const int l = l0 + p * nwarp;
+                float part = 0.f;
+#pragma unroll
+                for (int ai = 0; ai < 4; ++ai) part += v[lane + 32 * ai] * tanhf(sacc[p][ai]);
+                part = warp_sum(part);
+                if (lane == 0 && l < L) e[l] = l < len ? part : -INFINITY;
+            }
+        }
+    } else
     for (int l = warp; l < L; l += nwarp) {
         float part = 0.f;
         if (l < len) {
@@ -285,7 +343,7 @@ __device__ __forceinline__ void t2_attention_body(float* sm, int b, const float*
                     f += wloc_conv[k * NF + lane] * w_prev[l + k] + wloc_conv[(KL + k) * NF + lane] * w_cum[l + k];
             }
             for (int a = lane; a < A; a += 32) {
-                float s = q[a] + pmem[(static_cast<size_t>(b) * L + l) * A + a];
+                float s = q[a] + pmem_b[static_cast<size_t>(l) * A + a];
                 // wloc_dense is stored TRANSPOSED ([NF][A]): the lanes of a warp (consecutive a) read one line per filter
                 for (int nf = 0; nf < NF; ++nf) s += wloc_dense[nf * A + a] * __shfl_sync(0xffffffffu, f, nf);
                 part += v[a] * tanhf(s);
@@ -324,6 +382,26 @@ __device__ __forceinline__ void t2_attention_body(float* sm, int b, const float*
         align_out[b * L + l] = p;
     }
     __syncthreads();
+    if (q_in != nullptr && M <= static_cast<int>(blockDim.x)) {
+        // persistent decoder: the memory rows of 16 positions at a time are staged in shared memory by the whole CTA (one
+        // L2 round trip per 16 positions instead of one per 4), then every thread adds its column in position order — the
+        // same sequence of fused multiply-adds as the loop below
+        float* tile = ahs;                                    // [16][M] (the staged query input is not used in this mode)
+        const int m = threadIdx.x;
+        float acc = 0.f;
+        for (int l0 = 0; l0 < len; l0 += 16) {
+            const int nl = min(16, len - l0);
+            __syncthreads();
+            for (int i = threadIdx.x * 4; i < nl * M; i += blockDim.x * 4)
+                *reinterpret_cast<float4*>(tile + i) =
+                    __ldg(reinterpret_cast<const float4*>(memory + (static_cast<size_t>(b) * L + l0) * M + i));
+            __syncthreads();
+            if (m < M)
+                for (int l = 0; l < nl; ++l) acc += e[l0 + l] * tile[l * M + m];
+        }
+        if (m < M) ctx[static_cast<size_t>(b) * M + m] = acc;
+        return;
+    }
     for (int m = threadIdx.x; m < M; m += blockDim.x) {
         // loads of four positions are issued before their multiply-adds (same summation order, four L2 round trips in
         // flight instead of one per position)
@@ -412,6 +490,8 @@ struct T2PersistArgs {
     const int* lens;
     const float *memory, *pmem;
     float *ah[2], *ac, *dh[2], *dc, *aw, *awc, *ctx, *frame, *x, *gate, *frames, *align;
+    int att_off;                     // float offset of the staged attention tables in dynamic shared memory (0 = not staged)
+    float *q_buf, *x1;               // [B, A] query projections, [B, P] first prenet layer: written by all CTAs, read after a grid barrier
     int *finished, *mel_lens, *done_step;
     unsigned* bar;                   // grid barrier counter (zeroed before the launch)
     long long* timeline;             // debug (tools/t2_phases.py): CTA 0 and CTA B-1... accumulate cycles per phase, or null
@@ -533,6 +613,20 @@ __global__ void __launch_bounds__(512, 1) t2_decoder_persistent_kernel(const T2P
     unsigned n_bar = 0;
     const int lstm_blocks = a.H / 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    const int gw = blockIdx.x * nwarp + warp, GW = G * nwarp;      // this warp among all warps of the grid
+    // attention tables of this CTA's utterance, resident in shared memory for the whole launch (t2_attention_body)
+    const float* att_tables = nullptr;
+    if (a.att_off > 0 && a.B <= G && static_cast<int>(blockIdx.x) < a.B) {
+        float* t = sm + a.att_off;
+        const int n_conv = 2 * a.KL * a.NF, n_dense = a.NF * a.A, n_pm = a.L * a.A;
+        for (int i = threadIdx.x; i < n_conv; i += blockDim.x) t[i] = a.loc_conv[i];
+        for (int i = threadIdx.x; i < n_dense; i += blockDim.x) t[n_conv + i] = a.loc_dense[i];
+        for (int i = threadIdx.x; i < a.A; i += blockDim.x) t[n_conv + n_dense + i] = a.att_v[i];
+        for (int i = threadIdx.x; i < n_pm; i += blockDim.x)
+            t[n_conv + n_dense + a.A + i] = a.pmem[static_cast<size_t>(blockIdx.x) * n_pm + i];
+        att_tables = t;
+        __syncthreads();
+    }
     // prologue: the first step's prenet (later steps get theirs at the end of the previous step's phase D)
     for (int b = blockIdx.x; b < a.B; b += G)
         t2_prenet_body(sm, b, a.frame, a.pre_w0, a.pre_w1, a.masks, a.masks + static_cast<size_t>(a.B) * a.P, a.n_mel, a.P, a.x);
@@ -553,10 +647,18 @@ __global__ void __launch_bounds__(512, 1) t2_decoder_persistent_kernel(const T2P
         lap(0);
         t2_grid_barrier(a.bar, ++n_bar * G, a.err_flag);
         lap(1);
-        // B: location-sensitive attention, one utterance per CTA
+        // B1: query projections of all utterances, one dot product per warp of the whole grid (they were A / 16 sequential
+        // L2 round trips inside each utterance's CTA: tools/t2_phases.py)
+        for (int idx = gw; idx < a.B * a.A; idx += GW) {
+            const int b = idx / a.A, row = idx - b * a.A;
+            const float d = warp_dot_h<true>(a.w_query + static_cast<size_t>(row) * a.H, a.ah[nxt] + static_cast<size_t>(b) * a.H, a.H, lane);
+            if (lane == 0) a.q_buf[idx] = d;
+        }
+        t2_grid_barrier(a.bar, ++n_bar * G, a.err_flag);
+        // B2: location-sensitive attention, one utterance per CTA
         for (int b = blockIdx.x; b < a.B; b += G) {
             t2_attention_body(sm, b, a.ah[nxt], a.memory, a.pmem, a.lens, a.w_query, a.loc_conv, a.loc_dense, a.att_v, a.aw, a.awc,
-                              a.ctx, a.align + static_cast<size_t>(step) * a.B * a.L, a.L, a.H, a.M, a.A, a.NF, a.KL);
+                              a.ctx, a.align + static_cast<size_t>(step) * a.B * a.L, a.L, a.H, a.M, a.A, a.NF, a.KL, a.q_buf, att_tables);
             __syncthreads();
         }
         lap(2);
@@ -568,35 +670,42 @@ __global__ void __launch_bounds__(512, 1) t2_decoder_persistent_kernel(const T2P
         lap(4);
         t2_grid_barrier(a.bar, ++n_bar * G, a.err_flag);
         lap(5);
-        // D: mel frame + gate, stop bookkeeping, next prenet — per utterance, no grid barrier in between
-        for (int b = blockIdx.x; b < a.B; b += G) {
-            // [decoder hidden | context] of this utterance once into shared memory: 81 rows multiply it
-            float* hc = sm;
-            for (int k = threadIdx.x * 4; k < a.H + a.M; k += blockDim.x * 4)
-                *reinterpret_cast<float4*>(hc + k) = ld_state4(k < a.H ? a.dh[nxt] + static_cast<size_t>(b) * a.H + k
-                                                                       : a.ctx + static_cast<size_t>(b) * a.M + (k - a.H));
-            __syncthreads();
-            for (int o = warp; o <= a.n_mel; o += nwarp) {
-                const __half* wr = a.w_proj + static_cast<size_t>(o) * (a.H + a.M);
-                const float d = warp_dot_h(wr, hc, a.H, lane) + warp_dot_h(wr + a.H, hc + a.H, a.M, lane) + a.b_proj[o];
-                if (lane == 0) {
-                    if (o < a.n_mel) {
-                        a.frame[b * a.n_mel + o] = d;
-                        a.frames[(static_cast<size_t>(b) * a.max_steps + step) * a.n_mel + o] = d;
-                    } else {
-                        a.gate[b] = d;
-                        // mel_lens[~finished] += 1; finished |= sigmoid(gate) > thr   (torchaudio:846-849)
-                        if (!a.finished[b]) a.mel_lens[b] += 1;
-                        if (sigmoidf_(d) > a.gate_threshold) a.finished[b] = 1;
-                    }
+        // D1: mel frame + gate, one (utterance, output row) dot product per warp of the whole grid; the warp that owns a gate
+        // row does the stop bookkeeping. D2 / D3: the two prenet layers of the NEXT step, again one row per warp, a grid
+        // barrier between the layers. (One CTA per utterance ran these ~600 dot products as 40 sequential L2 round trips
+        // per warp: 29 % of the step.) Same warp_dot_h calls on the same values as the per-utterance bodies.
+        for (int idx = gw; idx < a.B * (a.n_mel + 1); idx += GW) {
+            const int b = idx / (a.n_mel + 1), o = idx - b * (a.n_mel + 1);
+            const __half* wr = a.w_proj + static_cast<size_t>(o) * (a.H + a.M);
+            const float d = warp_dot_h<true>(wr, a.dh[nxt] + static_cast<size_t>(b) * a.H, a.H, lane) +
+                            warp_dot_h<true>(wr + a.H, a.ctx + static_cast<size_t>(b) * a.M, a.M, lane) + a.b_proj[o];
+            if (lane == 0) {
+                if (o < a.n_mel) {
+                    a.frame[b * a.n_mel + o] = d;
+                    a.frames[(static_cast<size_t>(b) * a.max_steps + step) * a.n_mel + o] = d;
+                } else {
+                    a.gate[b] = d;
+                    // mel_lens[~finished] += 1; finished |= sigmoid(gate) > thr   (torchaudio:846-849)
+                    if (!a.finished[b]) a.mel_lens[b] += 1;
+                    if (sigmoidf_(d) > a.gate_threshold) a.finished[b] = 1;
                 }
             }
-            __syncthreads();                     // frame[b] complete (this CTA wrote it) before the prenet reads it
-            if (i + 1 < a.n_steps) {
-                const uint8_t* m0 = a.masks + (static_cast<size_t>(i + 1) * 2 + 0) * a.B * a.P;
-                t2_prenet_body(sm, b, a.frame, a.pre_w0, a.pre_w1, m0, m0 + static_cast<size_t>(a.B) * a.P, a.n_mel, a.P, a.x);
+        }
+        if (i + 1 < a.n_steps) {
+            const uint8_t* m0 = a.masks + (static_cast<size_t>(i + 1) * 2 + 0) * a.B * a.P;
+            const uint8_t* m1 = m0 + static_cast<size_t>(a.B) * a.P;
+            t2_grid_barrier(a.bar, ++n_bar * G, a.err_flag);
+            for (int idx = gw; idx < a.B * a.P; idx += GW) {
+                const int b = idx / a.P, o = idx - b * a.P;
+                const float d = warp_dot_h<true>(a.pre_w0 + static_cast<size_t>(o) * a.n_mel, a.frame + static_cast<size_t>(b) * a.n_mel, a.n_mel, lane);
+                if (lane == 0) a.x1[idx] = fmaxf(d, 0.f) * (m0[idx] ? 2.f : 0.f);
             }
-            __syncthreads();
+            t2_grid_barrier(a.bar, ++n_bar * G, a.err_flag);
+            for (int idx = gw; idx < a.B * a.P; idx += GW) {
+                const int b = idx / a.P, o = idx - b * a.P;
+                const float d = warp_dot_h<true>(a.pre_w1 + static_cast<size_t>(o) * a.P, a.x1 + static_cast<size_t>(b) * a.P, a.P, lane);
+                if (lane == 0) a.x[idx] = fmaxf(d, 0.f) * (m1[idx] ? 2.f : 0.f);
+            }
         }
         lap(6);
         t2_grid_barrier(a.bar, ++n_bar * G, a.err_flag);
@@ -780,7 +889,7 @@ namespace {
 
 struct T2State {   // device state of one batch, carved from the caller's state buffer
     int* lens; int* finished; int* mel_lens; int* done_step; unsigned* bar; int64_t* spk;
-    float *memory, *pmem, *ah[2], *ac, *dh[2], *dc, *aw, *awc, *ctx, *frame, *x, *gate, *frames, *align;
+    float *memory, *pmem, *ah[2], *ac, *dh[2], *dc, *aw, *awc, *ctx, *frame, *x, *gate, *frames, *align, *q_buf, *x1;
 };
 
 T2State carve_t2(const ttsb_tacotron2* h, void* p, int B, int L, int max_steps, size_t* bytes) {
@@ -798,6 +907,8 @@ T2State carve_t2(const ttsb_tacotron2* h, void* p, int B, int L, int max_steps, 
     s.x = c.take<float>(static_cast<size_t>(B) * h->P); s.gate = c.take<float>(B);
     s.frames = c.take<float>(static_cast<size_t>(B) * max_steps * h->n_mel);
     s.align = c.take<float>(static_cast<size_t>(max_steps) * B * L);
+    s.q_buf = c.take<float>(static_cast<size_t>(B) * h->A);
+    s.x1 = c.take<float>(static_cast<size_t>(B) * h->P);
     if (bytes) *bytes = c.off + 256;
     return s;
 }
@@ -1021,6 +1132,7 @@ int ttsb_tacotron2_decode(ttsb_tacotron2_t* h, int B, int L, int max_steps, int 
         a.masks = d_masks; a.lens = st.lens; a.memory = st.memory; a.pmem = st.pmem;
         a.ah[0] = st.ah[0]; a.ah[1] = st.ah[1]; a.ac = st.ac; a.dh[0] = st.dh[0]; a.dh[1] = st.dh[1]; a.dc = st.dc;
         a.aw = st.aw; a.awc = st.awc; a.ctx = st.ctx; a.frame = st.frame; a.x = st.x; a.gate = st.gate; a.frames = st.frames;
+        a.q_buf = st.q_buf; a.x1 = st.x1;
         a.align = st.align; a.finished = st.finished; a.mel_lens = st.mel_lens; a.done_step = st.done_step; a.bar = st.bar;
         ConvRuntime rt;
         TTSB_PROPAGATE(get_conv_runtime(0, rt));
@@ -1031,8 +1143,18 @@ int ttsb_tacotron2_decode(ttsb_tacotron2_t* h, int B, int L, int max_steps, int 
         a.arnn_b = h->arnn_b; a.drnn_b = h->drnn_b; a.loc_conv = h->loc_conv; a.loc_dense = h->loc_dense; a.att_v = h->att_v;
         a.b_proj = h->b_proj;
         const size_t lstm_smem = (8 * 4 * 64 + static_cast<size_t>(8) * (std::max(P, H) + M + H)) * sizeof(float);
-        const size_t smem = std::max({att_smem, static_cast<size_t>(h->n_mel + P) * sizeof(float), lstm_smem,
+        const size_t att_smem_p = (h->A + 2 * (L + h->KL) + L + 32 + 4 + std::max(h->H, 16 * M)) * sizeof(float);   // + the context tile
+        const size_t smem = std::max({att_smem_p, static_cast<size_t>(h->n_mel + P) * sizeof(float), lstm_smem,
                                       static_cast<size_t>(H + M) * sizeof(float)});
+        // + the attention tables (conv, dense, v, one utterance's processed memory) behind the phases' scratch, room permitting
+        const size_t tables = (static_cast<size_t>(2) * h->KL * h->NF + static_cast<size_t>(h->NF) * h->A + h->A +
+                               static_cast<size_t>(L) * h->A) * sizeof(float);
+        size_t smem_total = smem;
+        a.att_off = 0;
+        if (((smem + 15) & ~static_cast<size_t>(15)) + tables <= 200 * 1024) {
+            a.att_off = static_cast<int>(((smem + 15) & ~static_cast<size_t>(15)) / sizeof(float));
+            smem_total = a.att_off * sizeof(float) + tables;
+        }
         static PerDeviceOnce configured;
         if (!configured.here()) {
             TTSB_CHECK_CUDA(cudaFuncSetAttribute(t2_decoder_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -1040,14 +1162,14 @@ int ttsb_tacotron2_decode(ttsb_tacotron2_t* h, int B, int L, int max_steps, int 
         }
         TTSB_REQUIRE(smem <= 200 * 1024 && H % 8 == 0, "persistent decoder: shared-memory plan");
         int per_sm = 0;
-        TTSB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, t2_decoder_persistent_kernel, 512, smem));
+        TTSB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, t2_decoder_persistent_kernel, 512, smem_total));
         TTSB_REQUIRE(per_sm >= 1, "persistent decoder does not fit on an SM");
         // one CTA per SM; one pass over the LSTM's H/8 eight-unit blocks when the device has that many SMs
         const int grid = std::min(num_sms(), std::max(H / 8, B));
         TTSB_CHECK_CUDA(cudaMemsetAsync(st.bar, 0, 4 * sizeof(unsigned), s));
         void* kargs[] = {&a};
         TTSB_CHECK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(t2_decoder_persistent_kernel), dim3(grid), dim3(512),
-                                                    kargs, smem, s));
+                                                    kargs, smem_total, s));
         count_launch();
         if (h_done_step) {
             TTSB_CHECK_CUDA(cudaMemcpyAsync(h_done_step, st.done_step, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
