@@ -37,8 +37,8 @@ VOCODER_FLOP_PER_FRAME = 614.1e6
 # dram__bytes_read.sum + dram__bytes_write.sum over the generator launches of one 32768-frame pass, `ncu --set full`
 # (the capture named below); bench.py cannot read DRAM counters itself, so `roofline.traffic` = this per-frame figure x
 # the frames of a step. Re-captured whenever the generator's data flow changes.
-VOCODER_DRAM_BYTES_PER_FRAME = 54.49e9 / 32768
-VOCODER_DRAM_SOURCE = 'profiles/r02_s9_ncu_full_b64.csv (ncu --set full on the round-2 kernels, 33.21 GB read + 21.28 GB written per 32768-frame pass, per frame x frames)'
+VOCODER_DRAM_BYTES_PER_FRAME = 54.45e9 / 32768
+VOCODER_DRAM_SOURCE = 'profiles/r02_final_ncu_full_b64.csv (ncu --set full on the final round-2 kernels, 33.12 GB read + 21.33 GB written per 32768-frame pass, per frame x frames)'
 
 # csrc/common.cuh ProfTag
 PROF_TAGS = ['untagged', 'voc.conv_pre', 'voc.ups0', 'voc.s0', 'voc.ups1', 'voc.s1', 'voc.ups2', 'voc.s2', 'voc.ups3',
