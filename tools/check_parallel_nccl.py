@@ -34,8 +34,12 @@ def main():
     if rank == 0:
         ref, _ = tts.synthesize_ids(ids)
         ref = [w.clone() for w in ref]
-    for mode in ('nccl', 'nccl_host', 'host_shm'):
-        out, stats = parallel.synthesize(tts, ids, deliver=mode, return_stats=True)
+    for mode in ('nccl', 'nccl_host', 'host_shm', 'host_shm', 'host_shm_fallback'):
+        # host_shm twice: the second call reuses a persistent segment; then the fallback when no segment can be created
+        if mode == 'host_shm_fallback':
+            os.environ['TTSB_SHM_DISABLE'] = '1'
+            parallel._close_shm_pool()
+        out, stats = parallel.synthesize(tts, ids, deliver='host_shm' if mode.startswith('host_shm') else mode, return_stats=True)
         fr = torch.tensor([stats['frames'], stats['utterances']], dtype=torch.int64, device='cuda')
         allfr = [torch.empty_like(fr) for _ in range(world)]
         dist.all_gather(allfr, fr)

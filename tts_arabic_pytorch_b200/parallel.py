@@ -116,8 +116,20 @@ def _shm_segment(rank: int, dst: int, group, n_floats: int, dev) -> HostSharedBu
         name_t[0] = int.from_bytes(os.urandom(6), 'little')
     dist.broadcast(name_t, src=dst, group=group)
     name = 'ttsb_%x' % int(name_t[0])
-    buf = HostSharedBuffer(name, 1, cap, create=True) if rank == dst else None
-    dist.barrier(group=group)                # the segment exists
+    ok = torch.ones(1, dtype=torch.int64, device=dev)
+    buf = None
+    if rank == dst:
+        try:
+            import os
+            if os.environ.get('TTSB_SHM_DISABLE') == '1':          # tests: exercise the fallback
+                raise OSError('shared segment disabled')
+            buf = HostSharedBuffer(name, 1, cap, create=True)
+        except Exception:                    # e.g. /dev/shm too small: every rank falls back to the NCCL delivery
+            ok[0] = 0
+    dist.broadcast(ok, src=dst, group=group)  # (also orders creation before the attach below)
+    if int(ok[0]) == 0:
+        pool['bufs'][turn] = None
+        return None
     if rank != dst:
         buf = HostSharedBuffer(name, 1, cap, create=False)
     pool['bufs'][turn] = buf
@@ -156,6 +168,8 @@ def _synthesize_host_shm(model, id_list, shards, pad_to, rank, world, dst, group
         buf = _shm_segment(rank, dst, group, sum(sizes), dev)
         off = sum(sizes[:rank])
         state.update(buf=buf, rows_of=rows_of, cols_of=cols_of, sizes=sizes)
+        if buf is None:
+            return None                      # no shared segment: the waveforms stay on the device, NCCL delivers them
         return buf.tensor[0, off:off + b_local * n_cols].view(b_local, n_cols) if b_local else None
 
     if mine:
@@ -167,9 +181,25 @@ def _synthesize_host_shm(model, id_list, shards, pad_to, rank, world, dst, group
     else:
         frame_len_hook(0)                     # keep the collectives matched
         host_alloc(0, 1)
+        wav = torch.zeros(0, 1, dtype=torch.float32, device=dev)
         n_samples = torch.zeros(0, dtype=torch.int64, device=dev)
+        inverse = torch.zeros(0, dtype=torch.int64)
         info = torch.zeros(0, 2, dtype=torch.int64, device=dev)
     stats = {'frames': int(n_samples.sum()) // max(1, model.vocoder.hop), 'utterances': len(mine)}
+    if state['buf'] is None:
+        # fallback (the shared segment could not be created): padded NCCL gather + one device -> host copy on dst
+        rows = inverse.to(dev)
+        got = gather_waveforms(wav.index_select(0, rows), n_samples.index_select(0, rows), dst=dst, group=group)
+        res = None
+        if rank == dst:
+            per_rank = []
+            for w, c in zip(*got):
+                host = torch.empty(w.shape, dtype=w.dtype, pin_memory=True)
+                host.copy_(w, non_blocking=True)
+                torch.cuda.current_stream(dev).synchronize()
+                per_rank.append([host[k, :int(n)] for k, n in enumerate(c.tolist())])
+            res = unshard(per_rank, shards)
+        return (res, stats) if return_stats else res
     rows_of = state['rows_of']
     infos = [torch.empty(r * 2, dtype=torch.int64, device=dev) for r in rows_of]
     if len(set(rows_of)) == 1:
