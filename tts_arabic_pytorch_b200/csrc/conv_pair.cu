@@ -47,6 +47,7 @@ struct ConvPairArgs {
     int tt_pair;      // C = 32, resident W2: TT rows are 128 bytes [mid[t] | mid[t + 1]] and W2 comes as ceil(k / 2) tiles of
                       // 32 x 64 (taps 2g | 2g + 1): two taps per K = 64 group on 128-byte-swizzled operand rows (42 instead of
                       // 69 cycles per tcgen05.mma, profiles/r01_s21_mma_rate.txt); the mid epilogue writes every row twice
+    int c2_split;     // resident W2, two TT slots: warp 3 (idle then) issues conv2 of the ODD items, warp 2 of the even ones
     int w2_x2;        // streamed W2 only: one pass of the W2 ring feeds conv2 of TWO consecutive items (both TT slots, both acc2 buffers)
     int smem_res;     // 1: kernel instantiated with kSmemRes (host-side record; see conv_pair_forward)
     int in_act;       // 1: x is stored activated (lrelu(x)): the TMA panel IS conv1's operand — no in-place transform, the conv1
@@ -210,7 +211,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 if (++sx == args.x_slots) { sx = 0; px ^= 1; }
             }
         }
-    } else if (warp == 3) {
+    } else if (warp == 3 && !args.c2_split) {
         // ---------------- W2 ring producer (only when W2 does not fit next to W1) ----------------
         // its own warp: an x load must never queue behind W2 tiles that wait for conv2 to drain the ring
         if (!args.w2_resident && elect_one()) {
@@ -229,11 +230,15 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 }
             }
         }
-    } else if (warp == 1 || warp == 2) {
+    } else if (warp == 1 || warp == 2 || warp == 3) {
         // ---------------- MMA issuers: warp 1 issues every conv1, warp 2 every conv2 ----------------
         // Two threads because the per-item serial chain of ONE issuer (4 barrier waits, 2 x k MMAs, 4 commits)
         // was the tile period (profiles/r01_s25_pair_decomposition.txt); the tensor pipe interleaves both streams.
         // One elected thread each (see conv_tc2.cu on elect.sync).
+        // c2_split (resident W2, two TT slots): conv2 has THREE... two issuers of its own — warp 2 takes the even items
+        // (TT slot 0, acc2 buffer 0), warp 3 the odd ones (slot 1, buffer 1). tcgen05.mma issue blocks on the pipe, so one
+        // thread's (barrier waits + issue + commits) per item was the item period of the k = 3 pairs (round-2 session 31:
+        // ~1 360 + 380 of 1 750 cycles at C = 32); the two accumulators and TT slots are independent, so are the threads.
         if (elect_one()) {
             const uint32_t idesc = umma_idesc_f16(kTileM, C);
             const uint32_t row_u = row_bytes >> 4;
@@ -284,7 +289,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 const uint32_t tt_lo0 = (smem_u32(smem_tt) & 0x3FFFFu) >> 4;
                 const uint32_t w2_lo0 = (smem_u32(smem_w2) & 0x3FFFFu) >> 4;
                 const uint32_t ttp_u = ttp_bytes >> 4, ttslot_u = ttslot_bytes >> 4;
-                int st = 0, sb = 0, b2 = 0, it = 0;
+                const int split = args.c2_split ? 1 : 0;
+                const int me = split && warp == 3 ? 1 : 0;             // which half of the items this thread issues
+                const int step = split ? 2 * grid : grid;
+                int st = me, sb = 0, b2 = me, it = me;
                 uint32_t ptt = 0, pb = 0, pe2 = 3;
                 // Streamed W2, two items per pass. The ring (b_stages x one per-tap tile) delivers a tile every ~560 cycles
                 // whatever the consumer does (bytes in flight / copy latency: C = 64, k = 11 timelines), against 4 x 48 cycles of
@@ -335,7 +343,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     // panel shifted by 2g rows against W2's pair tile g; the last (odd) tap uses the first half only
                     const uint64_t desc_hi2 = (static_cast<uint64_t>(((8u * 128u) >> 4) | (1u << 14) | (2u << 29)) << 32) | (1u << 16);
                     const uint32_t b2tile_u = static_cast<uint32_t>(b2tile_bytes) >> 4;
-                    for (int idx = blockIdx.x; idx < args.n_work; idx += grid, ++it) {
+                    for (int idx = blockIdx.x + me * grid; idx < args.n_work; idx += step, it += split + 1) {
                         mbar_wait(&tt_full[st], (ptt >> st) & 1u, args.err_flag, 306);
                         mbar_wait(&acc2_empty[b2], (pe2 >> b2) & 1u, args.err_flag, 307);
                         pe2 ^= 1u << b2;
@@ -362,11 +370,13 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         umma_commit(&acc2_full[b2]);
                         tlp_mark(args, it, 6);
                         ptt ^= 1u << st;
-                        if (args.tt_slots == 2) st ^= 1;
-                        b2 ^= 1;
+                        if (!split) {
+                            if (args.tt_slots == 2) st ^= 1;
+                            b2 ^= 1;
+                        }
                     }
                 } else
-                for (int idx = blockIdx.x; idx < args.n_work; idx += grid, ++it) {
+                for (int idx = blockIdx.x + me * grid; idx < args.n_work; idx += step, it += split + 1) {
                     mbar_wait(&tt_full[st], (ptt >> st) & 1u, args.err_flag, 306);
                     mbar_wait(&acc2_empty[b2], (pe2 >> b2) & 1u, args.err_flag, 307);
                     pe2 ^= 1u << b2;
@@ -398,8 +408,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     umma_commit(&acc2_full[b2]);
                     tlp_mark(args, it, 6);
                     ptt ^= 1u << st;
-                    if (args.tt_slots == 2) st ^= 1;
-                    b2 ^= 1;
+                    if (!split) {
+                        if (args.tt_slots == 2) st ^= 1;
+                        b2 ^= 1;
+                    }
                 }
             }
         }
@@ -714,6 +726,10 @@ int conv_pair_forward(const ConvLayer& L1, const ConvLayer& L2, const ConvPairPl
     a.w2_resident = plan.w2_resident; a.b_stages = plan.b_stages;
     static const int want_w2_x2 = getenv("TTSB_PAIR_W2X2") ? atoi(getenv("TTSB_PAIR_W2X2")) : 1;
     a.w2_x2 = (want_w2_x2 && !plan.w2_resident && plan.tt_slots == 2) ? 1 : 0;
+    static const int want_c2_split = getenv("TTSB_PAIR_C2_SPLIT") ? atoi(getenv("TTSB_PAIR_C2_SPLIT")) : 1;
+    // measured (profiles/r02_s39_pair_two_conv2_issuers.txt): C = 32 pairs 1-5 % faster, C = 64 k = 7 5 % slower, the rest
+    // unchanged — the conv2 issue time is pipe latency under the epilogues' shared-memory traffic, not thread overhead
+    a.c2_split = (want_c2_split && plan.w2_resident && plan.tt_slots == 2 && (plan.C == 32 || want_c2_split >= 2)) ? 1 : 0;
     a.in_act = in_act ? 1 : 0;
     a.tt_pair = plan.tt_pair;
     a.w1 = L1.w_packed; a.w2 = plan.tt_pair ? L2.w_pair_packed : L2.w_packed;
